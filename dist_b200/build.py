@@ -1,0 +1,50 @@
+"""Build ``dist_b200/libdistb200.so`` (sm_100a only) in-tree with nvcc.
+
+The shared library is git-ignored but travels to the GPU box with the working tree.  ``build()``
+is a no-op when the library is newer than every source file.
+"""
+
+import glob
+import os
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libdistb200.so")
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "-Xcompiler", "-fPIC", "-shared",
+]
+
+
+def sources():
+    return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
+
+
+def _deps():
+    return sources() + glob.glob(os.path.join(CSRC, "*.cuh")) + [os.path.join(os.path.dirname(HERE), "include", "distb200.h")]
+
+
+def is_stale():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    return any(os.path.getmtime(p) > t for p in _deps())
+
+
+def build(force=False, verbose=False):
+    if not force and not is_stale():
+        return LIB
+    nvcc = os.environ.get("NVCC", "nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + sources()
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    if proc.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + proc.stdout + proc.stderr)
+    if verbose:
+        print(proc.stderr)
+    return LIB
+
+
+if __name__ == "__main__":
+    import sys
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,404 @@
+// distb200_gemm on the 5th-generation tensor cores (sm_100a): persistent, warp-specialised.
+//
+//   warp 0        TMA producer: cp.async.bulk.tensor tiles of A (4-D map, zero fill outside the tensor gives the
+//                 convolution halos / ragged edges for free) and B (3-D map: k, n, tap) into a ring of
+//                 128B-swizzled shared-memory stages, completion on mbarriers
+//   warp 1        MMA issuer: one elected lane issues tcgen05.mma (M=128, N=block_n, K=16, bf16 x bf16 -> fp32)
+//                 into one of two TMEM accumulator stages; tcgen05.commit releases smem stages and publishes
+//                 the finished accumulator
+//   warps 2..5    epilogue: tcgen05.ld (one accumulator row per thread), bias + residual + QuickGELU, fp32 and/or
+//                 bf16 stores with the row remapping of include/distb200.h (so the next tile's MMAs overlap it)
+//
+// Tile = rows_per_tile (<=128) output rows of one group x block_n columns; the reduction runs over
+// num_taps x ceil(K/64) k-blocks.  All rows of the 128-row MMA that lie outside the tile are computed on whatever
+// the smem holds and never stored.
+#include <cuda.h>
+
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace distb200 {
+
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;             // 64 bf16 = one 128-byte swizzle row
+constexpr int MAX_STAGES = 8;
+constexpr int NUM_THREADS = 192;
+constexpr uint32_t A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
+constexpr uint32_t TMEM_COLS = 512;
+constexpr uint32_t ACC_STAGE_COLS = 256;
+constexpr int SMEM_BUDGET = 200 * 1024;
+
+struct alignas(64) TcArgs {
+    CUtensorMap tm_a;
+    CUtensorMap tm_b;
+    distb200_gemm_desc d;
+    int block_n;
+    int stages;
+    int k_blocks;
+    int rows_per_tile;
+    int tiles_per_group;
+    int n_tiles;
+    int group_dim;
+    uint32_t b_stage_bytes;
+    uint32_t tx_bytes;
+    long long total_tiles;
+};
+
+struct TileCoord {
+    long long gi;
+    int r0;
+    int n0;
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const TcArgs& a, long long tile) {
+    TileCoord t;
+    const int n_idx = (int)(tile % a.n_tiles);
+    const long long m_idx = tile / a.n_tiles;
+    t.gi = m_idx / a.tiles_per_group;
+    t.r0 = (int)(m_idx % a.tiles_per_group) * a.rows_per_tile;
+    t.n0 = n_idx * a.block_n;
+    return t;
+}
+
+__device__ __forceinline__ void store_chunk16(const distb200_gemm_desc& d, const uint32_t* acc, int n, long long dst_row,
+                                              long long res_row) {
+    float v[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(acc[i]);
+    if (d.bias) {
+        const float4* bp = reinterpret_cast<const float4*>(d.bias + n);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float4 b4 = __ldg(bp + i);
+            v[4 * i + 0] += b4.x; v[4 * i + 1] += b4.y; v[4 * i + 2] += b4.z; v[4 * i + 3] += b4.w;
+        }
+    }
+    if (d.res) {
+        const float4* rp = reinterpret_cast<const float4*>(d.res + res_row * d.ld_res + n);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float4 r4 = rp[i];
+            v[4 * i + 0] += r4.x; v[4 * i + 1] += r4.y; v[4 * i + 2] += r4.z; v[4 * i + 3] += r4.w;
+        }
+    }
+    if (d.act == DISTB200_ACT_QUICKGELU) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = quick_gelu(v[i]);
+    }
+    if (d.out) {
+        if (d.out_dtype == DISTB200_F32) {
+            float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(d.out) + dst_row * d.ld_out + n);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) op[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        } else {
+            uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(d.out) + dst_row * d.ld_out + n);
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+                op[i] = make_uint4(pack_bf16x2(v[8 * i], v[8 * i + 1]), pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
+                                   pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
+        }
+    }
+    if (d.out2) {
+        if (d.out2_dtype == DISTB200_F32) {
+            float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(d.out2) + dst_row * d.ld_out2 + n);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) op[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        } else {
+            uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(d.out2) + dst_row * d.ld_out2 + n);
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+                op[i] = make_uint4(pack_bf16x2(v[8 * i], v[8 * i + 1]), pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
+                                   pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
+        }
+    }
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __grid_constant__ TcArgs args) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const distb200_gemm_desc& d = args.d;
+
+    // carve shared memory: [stages x (A | B)] [barriers] ; swizzle-128B needs 1024-byte aligned stage bases
+    const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t stage_bytes = A_STAGE_BYTES + args.b_stage_bytes;
+    const uint32_t bar_base = smem_base + (uint32_t)args.stages * stage_bytes;
+    // barriers (8 bytes each): full[MAX_STAGES], empty[MAX_STAGES], tmem_full[2], tmem_empty[2], then the TMEM base
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (MAX_STAGES + s); };
+    auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * MAX_STAGES + s); };
+    auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * MAX_STAGES + 2 + s); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * MAX_STAGES + 4);
+    uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - ptx::smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tensormap(&args.tm_a);
+        ptx::prefetch_tensormap(&args.tm_b);
+        for (int s = 0; s < args.stages; ++s) {
+            ptx::mbar_init(full_bar(s), 1);
+            ptx::mbar_init(empty_bar(s), 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            ptx::mbar_init(tfull_bar(s), 1);
+            ptx::mbar_init(tempty_bar(s), 4);
+        }
+        ptx::fence_barrier_init();
+    }
+    if (warp == 1) {
+        ptx::tmem_alloc(tmem_slot, TMEM_COLS);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    const int iters = d.num_taps * args.k_blocks;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (long long tile = blockIdx.x; tile < args.total_tiles; tile += gridDim.x) {
+                const TileCoord tc = decode_tile(args, tile);
+                for (int it = 0; it < iters; ++it) {
+                    const int tap = it / args.k_blocks;
+                    const int kb = it - tap * args.k_blocks;
+                    ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
+                    ptx::mbar_arrive_expect_tx(full_bar(stage), args.tx_bytes);
+                    const uint32_t sa = smem_base + (uint32_t)stage * stage_bytes;
+                    const uint32_t sb = sa + A_STAGE_BYTES;
+                    int c1, c2, c3;
+                    if (d.img_w > 0) {
+                        c1 = d.tap_off[tap][0];
+                        c2 = tc.r0 / d.img_w + d.tap_off[tap][1];
+                        c3 = (int)tc.gi + d.tap_off[tap][2];
+                    } else {
+                        c1 = tc.r0 + d.tap_off[tap][0];
+                        c2 = d.tap_off[tap][1] + (args.group_dim == 3 ? 0 : (int)tc.gi);
+                        c3 = d.tap_off[tap][2] + (args.group_dim == 3 ? (int)tc.gi : 0);
+                    }
+                    ptx::tma_load_4d(sa, &args.tm_a, full_bar(stage), kb * BLOCK_K, c1, c2, c3);
+                    ptx::tma_load_3d(sb, &args.tm_b, full_bar(stage), kb * BLOCK_K, tc.n0, tap);
+                    if (++stage == args.stages) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            const uint32_t idesc = ptx::umma_idesc_bf16(BLOCK_M, args.block_n);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc_stage = 0;
+            uint32_t acc_phase = 0;
+            for (long long tile = blockIdx.x; tile < args.total_tiles; tile += gridDim.x) {
+                ptx::mbar_wait(tempty_bar(acc_stage), acc_phase ^ 1u);
+                ptx::tc_fence_after();
+                const uint32_t tmem_d = tmem_base + (uint32_t)acc_stage * ACC_STAGE_COLS;
+                for (int it = 0; it < iters; ++it) {
+                    const int kb = it % args.k_blocks;
+                    ptx::mbar_wait(full_bar(stage), phase);
+                    ptx::tc_fence_after();
+                    const uint32_t sa = smem_base + (uint32_t)stage * stage_bytes;
+                    const uint64_t da = ptx::umma_desc_k_sw128(sa);
+                    const uint64_t db = ptx::umma_desc_k_sw128(sa + A_STAGE_BYTES);
+                    int ksteps = (d.k - kb * BLOCK_K + 15) / 16;
+                    ksteps = ksteps > BLOCK_K / 16 ? BLOCK_K / 16 : ksteps;
+                    for (int ks = 0; ks < ksteps; ++ks) {
+                        // advancing 16 bf16 (32 bytes) along K inside the swizzle row: +2 in the (addr >> 4) field
+                        ptx::mma_f16_ss(tmem_d, da + (uint64_t)(2 * ks), db + (uint64_t)(2 * ks), idesc, (it | ks) != 0);
+                    }
+                    ptx::mma_commit(empty_bar(stage));
+                    if (++stage == args.stages) { stage = 0; phase ^= 1u; }
+                }
+                ptx::mma_commit(tfull_bar(acc_stage));
+                if (++acc_stage == 2) { acc_stage = 0; acc_phase ^= 1u; }
+            }
+        }
+    } else {
+        // ===================== epilogue (4 warps = 128 accumulator rows) =====================
+        const int quad = warp & 3;              // TMEM lanes [32*quad, 32*quad+32) are the ones this warp may read
+        const int row = quad * 32 + lane;
+        int acc_stage = 0;
+        uint32_t acc_phase = 0;
+        for (long long tile = blockIdx.x; tile < args.total_tiles; tile += gridDim.x) {
+            const TileCoord tc = decode_tile(args, tile);
+            ptx::mbar_wait(tfull_bar(acc_stage), acc_phase);
+            ptx::tc_fence_after();
+            const long long r = (long long)tc.r0 + row;
+            const bool row_ok = row < args.rows_per_tile && r < d.rows_per_group;
+            const long long dst0 = tc.gi * d.out_gstride + d.out_roff + r;
+            const long long res0 = tc.gi * d.res_gstride + d.res_roff + r;
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)acc_stage * ACC_STAGE_COLS;
+            const int ncols = min(args.block_n, d.n - tc.n0);
+            for (int c0 = 0; c0 < ncols; c0 += 32) {
+                uint32_t acc[32];
+                const bool two = c0 + 16 < ncols;
+                ptx::tmem_ld16(taddr + (uint32_t)c0, acc);
+                if (two) ptx::tmem_ld16(taddr + (uint32_t)c0 + 16u, acc + 16);
+                ptx::tmem_ld_wait();
+                if (row_ok) {
+                    for (int rep = 0; rep < d.out_rep; ++rep) {
+                        const long long dr = dst0 + (long long)rep * d.out_rep_stride;
+                        const long long rr = res0 + (long long)rep * d.res_rep_stride;
+                        store_chunk16(d, acc, tc.n0 + c0, dr, rr);
+                        if (two) store_chunk16(d, acc + 16, tc.n0 + c0 + 16, dr, rr);
+                    }
+                }
+            }
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(tempty_bar(acc_stage));
+            if (++acc_stage == 2) { acc_stage = 0; acc_phase ^= 1u; }
+        }
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+// ---- host side ---------------------------------------------------------------------------------------
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+int make_map(CUtensorMap* tm, const void* base, int rank, const long long* dims, const long long* strides_elems,
+             const int* box, const char* what) {
+    EncodeTiledFn fn = encode_fn();
+    DISTB200_REQUIRE(fn != nullptr, "gemm(tcgen05): cuTensorMapEncodeTiled is not available from the driver");
+    cuuint64_t gdim[5];
+    cuuint64_t gstr[4];
+    cuuint32_t bdim[5], estr[5];
+    for (int i = 0; i < rank; ++i) {
+        gdim[i] = (cuuint64_t)dims[i];
+        bdim[i] = (cuuint32_t)box[i];
+        estr[i] = 1;
+        DISTB200_REQUIRE(dims[i] >= 1 && box[i] >= 1 && box[i] <= 256, "gemm(tcgen05): bad %s dim %d: size %lld box %d", what, i,
+                        dims[i], box[i]);
+    }
+    for (int i = 1; i < rank; ++i) {
+        long long s = strides_elems[i] * 2;
+        if (dims[i] == 1 && s < 16) s = (i > 1 ? (long long)gstr[i - 2] : 16);   // unused dimension: any legal stride
+        if (dims[i] == 1 && s % 16 != 0) s = 16;
+        DISTB200_REQUIRE(s % 16 == 0 && s > 0, "gemm(tcgen05): %s stride %d (%lld bytes) must be a positive multiple of 16", what, i, s);
+        gstr[i - 1] = (cuuint64_t)s;
+    }
+    DISTB200_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "gemm(tcgen05): %s base is not 16-byte aligned", what);
+    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bdim, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    DISTB200_REQUIRE(r == CUDA_SUCCESS, "gemm(tcgen05): cuTensorMapEncodeTiled(%s) failed with %d", what, (int)r);
+    return 0;
+}
+
+int pick_block_n(int n) {
+    if (n <= 256) return n;
+    for (int bn = 256; bn >= 64; bn -= 16)
+        if (n % bn == 0) return bn;
+    return 256;
+}
+
+}  // namespace
+
+int gemm_tcgen05_launch(const distb200_gemm_desc& d, cudaStream_t stream) {
+    const long long total_rows = d.groups * d.rows_per_group;
+    if (total_rows == 0 || d.n == 0) return 0;
+    DISTB200_REQUIRE(d.n % 16 == 0, "gemm(tcgen05): n=%d must be a multiple of 16", d.n);
+    DISTB200_REQUIRE(d.num_taps >= 1 && d.num_taps <= DISTB200_MAX_TAPS, "gemm(tcgen05): num_taps=%d", d.num_taps);
+    DISTB200_REQUIRE(d.a_stride[0] == 1, "gemm(tcgen05): a_stride[0] must be 1");
+    DISTB200_REQUIRE(d.ldb % 8 == 0 && d.b_tap_stride % 8 == 0, "gemm(tcgen05): ldb / b_tap_stride must be multiples of 8");
+    DISTB200_REQUIRE(!d.bias || (reinterpret_cast<uintptr_t>(d.bias) & 15) == 0, "gemm(tcgen05): bias must be 16-byte aligned");
+    DISTB200_REQUIRE(!d.res || ((reinterpret_cast<uintptr_t>(d.res) & 15) == 0 && d.ld_res % 4 == 0),
+                    "gemm(tcgen05): res must be 16-byte aligned with ld_res %% 4 == 0");
+    DISTB200_REQUIRE(!d.out || ((reinterpret_cast<uintptr_t>(d.out) & 15) == 0 && d.ld_out % 8 == 0),
+                    "gemm(tcgen05): out must be 16-byte aligned with ld_out %% 8 == 0");
+    DISTB200_REQUIRE(!d.out2 || ((reinterpret_cast<uintptr_t>(d.out2) & 15) == 0 && d.ld_out2 % 8 == 0),
+                    "gemm(tcgen05): out2 must be 16-byte aligned with ld_out2 %% 8 == 0");
+    DISTB200_REQUIRE(d.out_rep >= 1, "gemm(tcgen05): out_rep must be >= 1");
+
+    TcArgs args;
+    args.d = d;
+    args.group_dim = d.group_dim == 3 ? 3 : 2;
+    args.block_n = d.block_n > 0 ? d.block_n : pick_block_n(d.n);
+    DISTB200_REQUIRE(args.block_n % 16 == 0 && args.block_n >= 16 && args.block_n <= 256, "gemm(tcgen05): block_n=%d", args.block_n);
+    args.k_blocks = (d.k + BLOCK_K - 1) / BLOCK_K;
+    if (d.img_w > 0) {
+        DISTB200_REQUIRE(d.img_w <= BLOCK_M, "gemm(tcgen05): img_w=%d exceeds %d", d.img_w, BLOCK_M);
+        DISTB200_REQUIRE(d.rows_per_group % d.img_w == 0, "gemm(tcgen05): rows_per_group must be a multiple of img_w");
+        const int img_h = (int)(d.rows_per_group / d.img_w);
+        int rows_h = BLOCK_M / d.img_w;
+        if (rows_h > img_h) rows_h = img_h;
+        // balance the tiles of one image: e.g. 14 rows -> 2 tiles of 7 rather than 9 + 5
+        const int tiles = (img_h + rows_h - 1) / rows_h;
+        rows_h = (img_h + tiles - 1) / tiles;
+        args.rows_per_tile = rows_h * d.img_w;
+    } else {
+        args.rows_per_tile = BLOCK_M;
+    }
+    args.tiles_per_group = (int)((d.rows_per_group + args.rows_per_tile - 1) / args.rows_per_tile);
+    args.n_tiles = (d.n + args.block_n - 1) / args.block_n;
+    args.total_tiles = d.groups * args.tiles_per_group * args.n_tiles;
+    args.b_stage_bytes = (uint32_t)args.block_n * BLOCK_K * 2;
+    const uint32_t stage_bytes = A_STAGE_BYTES + args.b_stage_bytes;
+    args.stages = SMEM_BUDGET / (int)stage_bytes;
+    if (args.stages > MAX_STAGES) args.stages = MAX_STAGES;
+    if (args.stages < 2) args.stages = 2;
+
+    // A: (k, c1, c2, c3)
+    {
+        long long dims[4] = {d.a_dim[0], d.a_dim[1], d.a_dim[2], d.a_dim[3]};
+        long long str[4] = {1, d.a_stride[1], d.a_stride[2], d.a_stride[3]};
+        int box[4] = {BLOCK_K, 1, 1, 1};
+        if (d.img_w > 0) {
+            box[1] = d.img_w;
+            box[2] = args.rows_per_tile / d.img_w;
+        } else {
+            box[1] = args.rows_per_tile;
+        }
+        if (make_map(&args.tm_a, d.a, 4, dims, str, box, "A")) return 1;
+        args.tx_bytes = (uint32_t)(box[0] * box[1] * box[2] * box[3] * 2);
+    }
+    // B: (k, n, tap)
+    {
+        long long dims[3] = {d.k, d.n, d.num_taps};
+        long long str[3] = {1, d.ldb, d.num_taps > 1 ? d.b_tap_stride : d.ldb * d.n};
+        int box[3] = {BLOCK_K, args.block_n, 1};
+        if (make_map(&args.tm_b, d.b, 3, dims, str, box, "B")) return 1;
+        args.tx_bytes += (uint32_t)(BLOCK_K * args.block_n * 2);
+    }
+
+    const int smem = args.stages * (int)stage_bytes + 1024 + 8 * (2 * MAX_STAGES + 4) + 16;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        DISTB200_REQUIRE(e == cudaSuccess, "gemm(tcgen05): cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+        attr_done = true;
+    }
+    long long grid = args.total_tiles < sm_count() ? args.total_tiles : sm_count();
+    gemm_tcgen05_kernel<<<(unsigned)grid, NUM_THREADS, smem, stream>>>(args);
+    return check_launch("gemm_tcgen05");
+}
+
+}  // namespace distb200

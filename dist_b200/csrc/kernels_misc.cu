@@ -1,0 +1,328 @@
+// HBM-bound kernels of the path: LayerNorm(+cast), patchify, row broadcasts, frame means, single-query
+// cross attention and the class-score head.  One warp per row / per (batch, head); vectorised, coalesced
+// accesses; warp-shuffle reductions; fp32 statistics everywhere.
+#include "common.cuh"
+
+namespace distb200 {
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------------
+// LayerNorm: one warp per row, the row lives in registers (cols <= 32*4*MAXV).
+// ---------------------------------------------------------------------------------------------------
+constexpr int LN_MAXV = 8;   // float4 per lane -> cols <= 1024
+
+template <typename OutT>
+__device__ __forceinline__ void ln_store4(OutT* y, int c, float4 v);
+template <>
+__device__ __forceinline__ void ln_store4<float>(float* y, int c, float4 v) {
+    *reinterpret_cast<float4*>(y + c) = v;
+}
+template <>
+__device__ __forceinline__ void ln_store4<bf16>(bf16* y, int c, float4 v) {
+    *reinterpret_cast<uint2*>(y + c) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+}
+
+template <typename OutT>
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ in1, long long ld_in1,
+                                                        const float* __restrict__ in2, long long ld_in2, long long in2_period,
+                                                        long long rows, int cols, float eps,
+                                                        const float* __restrict__ g1, const float* __restrict__ b1, OutT* y1, long long ld_y1,
+                                                        const float* __restrict__ g2, const float* __restrict__ b2, OutT* y2, long long ld_y2) {
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const float* x = in1 + row * ld_in1;
+    const float* x2 = in2 ? in2 + (row % in2_period) * ld_in2 : nullptr;
+    float4 v[LN_MAXV];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i) {
+        const int c = (i * 32 + lane) * 4;
+        if (c < cols) {
+            v[i] = *reinterpret_cast<const float4*>(x + c);
+            if (x2) {
+                const float4 w = *reinterpret_cast<const float4*>(x2 + c);
+                v[i].x += w.x; v[i].y += w.y; v[i].z += w.z; v[i].w += w.w;
+            }
+            sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+        }
+    }
+    const float mean = warp_sum(sum) / (float)cols;
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i) {
+        const int c = (i * 32 + lane) * 4;
+        if (c < cols) {
+            const float a = v[i].x - mean, b = v[i].y - mean, cc = v[i].z - mean, dd = v[i].w - mean;
+            sq += (a * a + b * b) + (cc * cc + dd * dd);
+        }
+    }
+    const float rstd = rsqrtf(warp_sum(sq) / (float)cols + eps);
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i) {
+        const int c = (i * 32 + lane) * 4;
+        if (c < cols) {
+            float4 n;
+            n.x = (v[i].x - mean) * rstd; n.y = (v[i].y - mean) * rstd;
+            n.z = (v[i].z - mean) * rstd; n.w = (v[i].w - mean) * rstd;
+            const float4 ga = *reinterpret_cast<const float4*>(g1 + c), be = *reinterpret_cast<const float4*>(b1 + c);
+            ln_store4<OutT>(y1 + row * ld_y1, c, make_float4(n.x * ga.x + be.x, n.y * ga.y + be.y, n.z * ga.z + be.z, n.w * ga.w + be.w));
+            if (y2) {
+                const float4 gb = *reinterpret_cast<const float4*>(g2 + c), bb = *reinterpret_cast<const float4*>(b2 + c);
+                ln_store4<OutT>(y2 + row * ld_y2, c, make_float4(n.x * gb.x + bb.x, n.y * gb.y + bb.y, n.z * gb.z + bb.z, n.w * gb.w + bb.w));
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// patchify: one thread per pixel pair; reads are contiguous along image rows, writes are 2*esize contiguous.
+// ---------------------------------------------------------------------------------------------------
+template <typename OutT>
+__global__ void __launch_bounds__(256) patchify_kernel(const float* __restrict__ video, OutT* __restrict__ out, int clips, int T, int H, int W,
+                                                       int p, int first, int step, int n_sel, long long ld_out) {
+    const int g = W / p;
+    const int halfW = W >> 1;
+    const long long total = (long long)clips * n_sel * 3 * H * halfW;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int xh = (int)(idx % halfW);
+        long long rest = idx / halfW;
+        const int y = (int)(rest % H); rest /= H;
+        const int c = (int)(rest % 3); rest /= 3;
+        const int i = (int)(rest % n_sel);
+        const int clip = (int)(rest / n_sel);
+        const int x = xh * 2;
+        const int frame = first + i * step;
+        const float2 px = *reinterpret_cast<const float2*>(video + ((((long long)clip * 3 + c) * T + frame) * H + y) * W + x);
+        const int pr = y / p, iy = y - pr * p, pc = x / p, ix = x - pc * p;
+        const long long orow = ((long long)clip * n_sel + i) * (g * g) + pr * g + pc;
+        OutT* o = out + orow * ld_out + (c * p + iy) * p + ix;
+        o[0] = from_float<OutT>(px.x);
+        o[1] = from_float<OutT>(px.y);
+    }
+}
+
+template <typename OutT>
+__global__ void zero_pad_cols_kernel(OutT* out, long long rows, int c0, long long ld) {
+    const int pad = (int)ld - c0;
+    const long long total = rows * pad;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x)
+        out[(idx / pad) * ld + c0 + (idx % pad)] = from_float<OutT>(0.f);
+}
+
+// ---------------------------------------------------------------------------------------------------
+__global__ void rows_bcast_kernel(float* dst, long long row_stride, long long n_rows, int cols, const float* __restrict__ table,
+                                  long long period, int accumulate) {
+    const long long total = n_rows * cols;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const long long i = idx / cols;
+        const int c = (int)(idx % cols);
+        const float t = table[(i % period) * cols + c];
+        float* p = dst + i * row_stride + c;
+        *p = accumulate ? *p + t : t;
+    }
+}
+
+template <typename OutT>
+__global__ void mean_rows_kernel(const float* __restrict__ src, long long row_stride, int count, long long batch, int cols, OutT* out) {
+    const long long total = batch * cols;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const long long b = idx / cols;
+        const int c = (int)(idx % cols);
+        float s = 0.f;
+        for (int i = 0; i < count; ++i) s += src[(b * count + i) * row_stride + c];
+        out[idx] = from_float<OutT>(s / (float)count);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// single-query cross attention: one warp per (batch element, head); head dim 64 = 2 dims per lane.
+// ---------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(128) cross_attention_kernel(const T* __restrict__ q, const T* __restrict__ kv, T* __restrict__ out,
+                                                              int batch, int keys, int heads) {
+    extern __shared__ float sc_all[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5;
+    const long long item = (long long)blockIdx.x * wpb + warp;
+    if (item >= (long long)batch * heads) return;
+    float* sc = sc_all + (size_t)warp * keys;
+    const int b = (int)(item / heads), h = (int)(item % heads);
+    const int C = heads * 64;
+    const float q0 = to_float(q[(long long)b * C + h * 64 + lane * 2]) * 0.125f;
+    const float q1 = to_float(q[(long long)b * C + h * 64 + lane * 2 + 1]) * 0.125f;
+    const T* kbase = kv + (long long)b * keys * 2 * C + h * 64 + lane * 2;
+    float mx = -INFINITY;
+    for (int j = 0; j < keys; ++j) {
+        const T* kp = kbase + (long long)j * 2 * C;
+        float s = q0 * to_float(kp[0]) + q1 * to_float(kp[1]);
+        s = warp_sum(s);
+        if (lane == 0) sc[j] = s;
+        mx = fmaxf(mx, s);
+    }
+    __syncwarp();
+    float den = 0.f;
+    for (int j = lane; j < keys; j += 32) {
+        const float e = __expf(sc[j] - mx);
+        sc[j] = e;
+        den += e;
+    }
+    den = warp_sum(den);
+    __syncwarp();
+    float o0 = 0.f, o1 = 0.f;
+    const T* vbase = kbase + C;
+    for (int j = 0; j < keys; ++j) {
+        const T* vp = vbase + (long long)j * 2 * C;
+        const float pj = sc[j];
+        o0 = fmaf(pj, to_float(vp[0]), o0);
+        o1 = fmaf(pj, to_float(vp[1]), o1);
+    }
+    const float inv = 1.f / den;
+    out[(long long)b * C + h * 64 + lane * 2] = from_float<T>(o0 * inv);
+    out[(long long)b * C + h * 64 + lane * 2 + 1] = from_float<T>(o1 * inv);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// class head: one block per clip.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) class_head_kernel(const float* __restrict__ emb, const float* __restrict__ text_n, float scale,
+                                                         int E, int C, float* logits, float* probs) {
+    extern __shared__ float sh[];          // [E] embedding, [C] logits, [32] scratch
+    float* se = sh;
+    float* sl = sh + E;
+    float* red = sl + C;
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+    float ss = 0.f;
+    for (int e = tid; e < E; e += blockDim.x) {
+        const float v = emb[(long long)b * E + e];
+        se[e] = v;
+        ss += v * v;
+    }
+    ss = warp_sum(ss);
+    if (lane == 0) red[warp] = ss;
+    __syncthreads();
+    float tot = 0.f;
+    for (int w = 0; w < nw; ++w) tot += red[w];
+    const float inv = scale * rsqrtf(tot);
+    __syncthreads();
+    for (int c = warp; c < C; c += nw) {
+        float dot = 0.f;
+        for (int e = lane; e < E; e += 32) dot = fmaf(se[e], text_n[(long long)c * E + e], dot);
+        dot = warp_sum(dot);
+        if (lane == 0) {
+            sl[c] = dot * inv;
+            if (logits) logits[(long long)b * C + c] = dot * inv;
+        }
+    }
+    __syncthreads();
+    if (!probs) return;
+    float mx = -INFINITY;
+    for (int c = tid; c < C; c += blockDim.x) mx = fmaxf(mx, sl[c]);
+    mx = warp_max(mx);
+    if (lane == 0) red[warp] = mx;
+    __syncthreads();
+    mx = red[0];
+    for (int w = 1; w < nw; ++w) mx = fmaxf(mx, red[w]);
+    __syncthreads();
+    float den = 0.f;
+    for (int c = tid; c < C; c += blockDim.x) den += __expf(sl[c] - mx);
+    den = warp_sum(den);
+    if (lane == 0) red[warp] = den;
+    __syncthreads();
+    den = 0.f;
+    for (int w = 0; w < nw; ++w) den += red[w];
+    for (int c = tid; c < C; c += blockDim.x) probs[(long long)b * C + c] = __expf(sl[c] - mx) / den;
+}
+
+inline unsigned grid_for(long long total, int block) {
+    long long g = (total + block - 1) / block;
+    const long long cap = (long long)sm_count() * 16;
+    return (unsigned)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace
+
+}  // namespace distb200
+
+using namespace distb200;
+
+extern "C" int distb200_layernorm(const float* in1, int64_t ld_in1, const float* in2, int64_t ld_in2, int64_t in2_period,
+                                  int64_t rows, int32_t cols, float eps, const float* g1, const float* b1, void* y1, int64_t ld_y1,
+                                  const float* g2, const float* b2, void* y2, int64_t ld_y2, int32_t out_dtype, void* stream) {
+    if (rows == 0) return 0;
+    DISTB200_REQUIRE(cols % 4 == 0 && cols <= 128 * LN_MAXV, "layernorm: cols=%d must be a multiple of 4 and <= %d", cols, 128 * LN_MAXV);
+    DISTB200_REQUIRE(ld_in1 % 4 == 0 && ld_y1 % 4 == 0 && (!in2 || ld_in2 % 4 == 0) && (!y2 || ld_y2 % 4 == 0), "layernorm: row pitches must be multiples of 4");
+    DISTB200_REQUIRE(in1 && g1 && b1 && y1, "layernorm: null pointer");
+    DISTB200_REQUIRE(!y2 || (g2 && b2), "layernorm: second affine parameters missing");
+    if (!in2) in2_period = 1;
+    DISTB200_REQUIRE(in2_period >= 1, "layernorm: in2_period must be >= 1");
+    const int wpb = 8;
+    const unsigned grid = (unsigned)((rows + wpb - 1) / wpb);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (out_dtype == DISTB200_F32)
+        layernorm_kernel<float><<<grid, wpb * 32, 0, st>>>(in1, ld_in1, in2, ld_in2, in2_period, rows, cols, eps, g1, b1, (float*)y1, ld_y1, g2, b2, (float*)y2, ld_y2);
+    else
+        layernorm_kernel<bf16><<<grid, wpb * 32, 0, st>>>(in1, ld_in1, in2, ld_in2, in2_period, rows, cols, eps, g1, b1, (bf16*)y1, ld_y1, g2, b2, (bf16*)y2, ld_y2);
+    return check_launch("layernorm");
+}
+
+extern "C" int distb200_patchify(const float* video, void* out, int32_t clips, int32_t T, int32_t H, int32_t W, int32_t p,
+                                 int32_t first_frame, int32_t frame_step, int32_t n_sel, int64_t ld_out, int32_t out_dtype, void* stream) {
+    DISTB200_REQUIRE(H % p == 0 && W % p == 0 && W % 2 == 0 && p % 2 == 0, "patchify: H=%d W=%d p=%d", H, W, p);
+    DISTB200_REQUIRE(first_frame >= 0 && frame_step >= 1 && first_frame + (n_sel - 1) * frame_step < T, "patchify: frame selection out of range");
+    DISTB200_REQUIRE(ld_out >= 3 * p * p, "patchify: ld_out too small");
+    const long long total = (long long)clips * n_sel * 3 * H * (W / 2);
+    if (total == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long rows = (long long)clips * n_sel * (H / p) * (W / p);
+    if (out_dtype == DISTB200_F32) {
+        patchify_kernel<float><<<grid_for(total, 256), 256, 0, st>>>(video, (float*)out, clips, T, H, W, p, first_frame, frame_step, n_sel, ld_out);
+        if (ld_out > 3 * p * p) zero_pad_cols_kernel<float><<<grid_for(rows * (ld_out - 3 * p * p), 256), 256, 0, st>>>((float*)out, rows, 3 * p * p, ld_out);
+    } else {
+        patchify_kernel<bf16><<<grid_for(total, 256), 256, 0, st>>>(video, (bf16*)out, clips, T, H, W, p, first_frame, frame_step, n_sel, ld_out);
+        if (ld_out > 3 * p * p) zero_pad_cols_kernel<bf16><<<grid_for(rows * (ld_out - 3 * p * p), 256), 256, 0, st>>>((bf16*)out, rows, 3 * p * p, ld_out);
+    }
+    return check_launch("patchify");
+}
+
+extern "C" int distb200_rows_bcast(float* dst, int64_t row_stride, int64_t n_rows, int32_t cols, const float* table, int64_t period,
+                                   int32_t accumulate, void* stream) {
+    if (n_rows == 0 || cols == 0) return 0;
+    DISTB200_REQUIRE(period >= 1, "rows_bcast: period must be >= 1");
+    rows_bcast_kernel<<<grid_for(n_rows * cols, 256), 256, 0, (cudaStream_t)stream>>>(dst, row_stride, n_rows, cols, table, period, accumulate);
+    return check_launch("rows_bcast");
+}
+
+extern "C" int distb200_mean_rows(const float* src, int64_t row_stride, int32_t count, int64_t batch, int32_t cols, void* out,
+                                  int32_t out_dtype, void* stream) {
+    if (batch == 0 || cols == 0) return 0;
+    DISTB200_REQUIRE(count >= 1, "mean_rows: count must be >= 1");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (out_dtype == DISTB200_F32) mean_rows_kernel<float><<<grid_for(batch * cols, 256), 256, 0, st>>>(src, row_stride, count, batch, cols, (float*)out);
+    else mean_rows_kernel<bf16><<<grid_for(batch * cols, 256), 256, 0, st>>>(src, row_stride, count, batch, cols, (bf16*)out);
+    return check_launch("mean_rows");
+}
+
+extern "C" int distb200_cross_attention(const void* q, const void* kv, void* out, int32_t batch, int32_t keys, int32_t heads,
+                                        int32_t dtype, void* stream) {
+    if (batch == 0) return 0;
+    DISTB200_REQUIRE(keys >= 1 && keys <= 2048, "cross_attention: keys=%d out of range", keys);
+    const int wpb = 4;
+    const long long items = (long long)batch * heads;
+    const unsigned grid = (unsigned)((items + wpb - 1) / wpb);
+    const size_t smem = (size_t)wpb * keys * sizeof(float);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == DISTB200_F32) cross_attention_kernel<float><<<grid, wpb * 32, smem, st>>>((const float*)q, (const float*)kv, (float*)out, batch, keys, heads);
+    else cross_attention_kernel<bf16><<<grid, wpb * 32, smem, st>>>((const bf16*)q, (const bf16*)kv, (bf16*)out, batch, keys, heads);
+    return check_launch("cross_attention");
+}
+
+extern "C" int distb200_class_head(const float* emb, const float* text_n, float scale, int32_t batch, int32_t embed_dim, int32_t classes,
+                                   float* logits, float* probs, void* stream) {
+    if (batch == 0) return 0;
+    const size_t smem = (size_t)(embed_dim + classes + 32) * sizeof(float);
+    DISTB200_REQUIRE(smem <= 48 * 1024, "class_head: E + C too large for one block (%zu bytes)", smem);
+    class_head_kernel<<<batch, 256, smem, (cudaStream_t)stream>>>(emb, text_n, scale, embed_dim, classes, logits, probs);
+    return check_launch("class_head");
+}

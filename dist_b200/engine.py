@@ -1,0 +1,386 @@
+"""Forward engine of the DiST video path on the distb200 CUDA library.
+
+``DistEngine`` packs a reference-format ``state_dict`` once (bf16 or fp32 operands, convolution weights
+re-laid as per-tap K-major matrices), allocates every activation buffer for a fixed clip count, and
+*plans* the whole forward as a flat list of prepared C calls (``ops.Call``).  Running the model is
+replaying that list on a stream - directly, or as a captured CUDA graph.  No torch operator runs on
+the hot path; PyTorch only provides device memory and streams.
+
+Data layout (HBM), b clips, T dense / t = T/alpha sparse frames, N = P+1 tokens:
+  ViT stream            h      [b*t*N, D]   fp32   frame-major tokens, frame = clip*t + ti, token 0 = class
+  temporal stream       xT     [b*T*P, Ct]  fp32   channels-last (clip, frame, row, col)
+  integration stream    mid    [b*t*N, Ci]  fp32   (becomes ``upd`` in place), ``res`` alike
+  GEMM operands         bf16 (or fp32 on the parity path) copies written by the producing kernel's epilogue
+
+Semantics follow SURVEY.md section 8(a'); the reference lines are cited next to each step.
+"""
+
+import math
+
+import torch
+
+from . import ops
+from .arch import DistArch
+
+
+def _pad8(n):
+    return (n + 7) // 8 * 8
+
+
+class PackedWeights:
+    """Device-resident, kernel-ready weights (reference key names in the comments)."""
+
+    def __init__(self, sd, arch: DistArch, device, act_dtype):
+        self.arch, self.device, self.adt = arch, device, act_dtype
+        a = arch
+        f32 = lambda x: x.detach().to(device=device, dtype=torch.float32).contiguous()
+        op = lambda x: x.detach().to(device=device, dtype=torch.float32).contiguous().to(act_dtype)
+
+        def padk(w2d, kp):
+            n, k = w2d.shape
+            if k == kp:
+                return op(w2d)
+            out = torch.zeros(n, kp, dtype=torch.float32)
+            out[:, :k] = w2d.detach().float().cpu()
+            return op(out)
+
+        D, L, p = a.width, a.layers, a.patch
+        self.kp = _pad8(3 * p * p)
+        self.conv1_w = padk(sd["visual.conv1.weight"].reshape(D, -1), self.kp)                 # clip.py:243
+        pos = sd["visual.positional_embedding"].float()
+        self.pos = f32(pos)                                                                    # [N, D]
+        self.cls_row = f32((sd["visual.class_embedding"].float() + pos[0]).reshape(1, D))      # clip.py:274-275
+        self.ln_pre = (f32(sd["visual.ln_pre.weight"]), f32(sd["visual.ln_pre.bias"]))
+        self.vit = []
+        for l in range(L):
+            pre = "visual.transformer.resblocks.%d." % l
+            self.vit.append(dict(
+                ln1=(f32(sd[pre + "ln_1.weight"]), f32(sd[pre + "ln_1.bias"])),
+                qkv_w=op(sd[pre + "attn.in_proj_weight"]), qkv_b=f32(sd[pre + "attn.in_proj_bias"]),
+                proj_w=op(sd[pre + "attn.out_proj.weight"]), proj_b=f32(sd[pre + "attn.out_proj.bias"]),
+                ln2=(f32(sd[pre + "ln_2.weight"]), f32(sd[pre + "ln_2.bias"])),
+                fc1_w=op(sd[pre + "mlp.c_fc.weight"]), fc1_b=f32(sd[pre + "mlp.c_fc.bias"]),
+                fc2_w=op(sd[pre + "mlp.c_proj.weight"]), fc2_b=f32(sd[pre + "mlp.c_proj.bias"]),
+            ))
+
+        # ---- DiST ----
+        Ci, Ct, ps = a.integration_dim, a.temporal_dim, a.s_patch
+        self.kps = _pad8(3 * ps * ps)
+        w = sd["dist_net.temporal_stem.weight"].float()                                        # [Ct, 3, kt, ps, ps]
+        w = w.permute(2, 0, 1, 3, 4).reshape(a.t_patch, Ct, 3 * ps * ps)
+        self.stem_w = torch.stack([padk(w[k], self.kps) for k in range(a.t_patch)]).contiguous()   # [kt, Ct, Kp]
+        self.stem_b = f32(sd["dist_net.temporal_stem.bias"])
+        self.dist = []
+        for i in range(len(a.selected_layers)):
+            tn, it = "dist_net.temporal_nets.%d." % i, "dist_net.integration_nets.%d." % i
+            t2i, i2t = "dist_net.temporal2integration_nets.%d." % i, "dist_net.integration2temporal_nets.%d." % i
+            w1 = sd[tn + "temporal_net.c_fc1.weight"].float()[:, :, :, 0, 0].permute(2, 0, 1)     # [kt, Ch, Ct]
+            w2 = sd[tn + "temporal_net.c_fc2.weight"].float()[:, :, 0].permute(2, 3, 0, 1)        # [3, 3, Ct, Ch]
+            wt = sd[t2i + "linear_fuse.weight"].float()[:, :, :, 0, 0].permute(2, 0, 1)           # [alpha, Ci, Ct]
+            wk = sd[it + "temporal_ffn.c_fc2.weight"].float()[:, :, :, 0, 0].permute(2, 0, 1)      # [kt, Cm, Cm]
+            self.dist.append(dict(
+                tn_ln=(f32(sd[tn + "ln.weight"]), f32(sd[tn + "ln.bias"])),
+                tn_w1=op(w1), tn_b1=f32(sd[tn + "temporal_net.c_fc1.bias"]),
+                tn_w2=op(w2.reshape(9, w2.shape[2], w2.shape[3])), tn_b2=f32(sd[tn + "temporal_net.c_fc2.bias"]),
+                in_w=op(sd["dist_net.input_linears.%d.weight" % i]), in_b=f32(sd["dist_net.input_linears.%d.bias" % i]),
+                i2t_w=op(sd[i2t + "linear_fuse.weight"]), i2t_b=f32(sd[i2t + "linear_fuse.bias"]),
+                t2i_w=op(wt), t2i_b=f32(sd[t2i + "linear_fuse.bias"]),
+                t2i_cls=f32(sd[t2i + "cls_token"].float().reshape(a.sparse_frames, Ci)),
+                ln=(f32(sd[it + "ln.weight"]), f32(sd[it + "ln.bias"])),
+                ln_t=(f32(sd[it + "ln_temporal.weight"]), f32(sd[it + "ln_temporal.bias"])),
+                fc_w=op(sd[it + "ffn.c_fc.weight"]), fc_b=f32(sd[it + "ffn.c_fc.bias"]),
+                pr_w=op(sd[it + "ffn.c_proj.weight"]), pr_b=f32(sd[it + "ffn.c_proj.bias"]),
+                tf1_w=op(sd[it + "temporal_ffn.c_fc1.weight"].float()[:, :, 0, 0, 0]), tf1_b=f32(sd[it + "temporal_ffn.c_fc1.bias"]),
+                tf2_w=op(wk), tf2_b=f32(sd[it + "temporal_ffn.c_fc2.bias"]),
+                tf3_w=op(sd[it + "temporal_ffn.c_proj.weight"].float()[:, :, 0, 0, 0]), tf3_b=f32(sd[it + "temporal_ffn.c_proj.bias"]),
+            ))
+        self.ada = []
+        for j in range(a.ada_layers):
+            pre = "dist_net.adapooling_nets.%d." % j
+            entry = dict(pos=f32(sd[pre + "positional_embedding"].float().reshape(a.sparse_frames, Ci)))
+            for tag, which, ln_out, mlp in (("sp", "spatial_transformer", "ln_out_spat_cls_token", "output_map_spatial_cls_token"),
+                                            ("tp", "temporal_transformer", "ln_out_temp_cls_token", "output_map_cls_token")):
+                wq = sd[pre + which + ".attn.in_proj_weight"].float()
+                bq = sd[pre + which + ".attn.in_proj_bias"].float()
+                entry[tag] = dict(
+                    ln=(f32(sd[pre + which + ".ln_1.weight"]), f32(sd[pre + which + ".ln_1.bias"])),
+                    q_w=op(wq[:Ci]), q_b=f32(bq[:Ci]), kv_w=op(wq[Ci:]), kv_b=f32(bq[Ci:]),
+                    o_w=op(sd[pre + which + ".attn.out_proj.weight"]), o_b=f32(sd[pre + which + ".attn.out_proj.bias"]),
+                    ln_out=(f32(sd[pre + ln_out + ".weight"]), f32(sd[pre + ln_out + ".bias"])),
+                    fc_w=op(sd[pre + mlp + ".c_fc.weight"]), fc_b=f32(sd[pre + mlp + ".c_fc.bias"]),
+                    pr_w=op(sd[pre + mlp + ".c_proj.weight"]), pr_b=f32(sd[pre + mlp + ".c_proj.bias"]),
+                )
+            self.ada.append(entry)
+        self.agg_cls = f32(sd["dist_net.aggregated_cls_token"].float().reshape(1, Ci))
+        self.agg_sp = f32(sd["dist_net.aggregated_spatial_cls_token"].float().reshape(1, Ci))
+        self.pcls_w = op(sd["dist_net.proj_spatial_cls_token.weight"])
+        self.pcls_b = f32(sd["dist_net.proj_spatial_cls_token.bias"])
+        self.ln_post = (f32(sd["dist_net.ln_post.weight"]), f32(sd["dist_net.ln_post.bias"]))
+        self.proj_w = op(sd["dist_net.proj"].float().t())                                       # [E, Ci]
+        self.logit_scale = float(sd["logit_scale"].float().exp()) if "logit_scale" in sd else 1.0 / 0.07
+
+
+class DistEngine:
+    """Planned forward for a fixed number of clips per call."""
+
+    def __init__(self, state_dict, arch: DistArch, batch, device="cuda", precision="bf16", text_features=None,
+                 gemm_impl=ops.IMPL_AUTO, attn_impl=ops.IMPL_AUTO):
+        assert precision in ("bf16", "fp32")
+        arch.validate()
+        ops.lib()     # fail loudly before touching the GPU if the extension is missing
+        self.arch, self.batch, self.device, self.precision = arch, int(batch), torch.device(device), precision
+        self.adt = torch.bfloat16 if precision == "bf16" else torch.float32
+        self.gemm_impl, self.attn_impl = gemm_impl, attn_impl
+        self.w = PackedWeights(state_dict, arch, self.device, self.adt)
+        self.text_n = None
+        if text_features is not None:
+            self.set_text_features(text_features)
+        self._alloc()
+        self.calls = []
+        self._plan()
+        self.graph = None
+
+    # ------------------------------------------------------------------------------------------
+    def set_text_features(self, feats):
+        """Cached label embeddings [C, E] (clip.py:437-452); normalised once (clip.py:514)."""
+        f = feats.detach().to(device=self.device, dtype=torch.float32)
+        self.text_n = (f / f.norm(dim=1, keepdim=True)).contiguous()
+        if hasattr(self, "logits") and self.text_n.shape[0] != self.logits.shape[1]:
+            raise ValueError("text features changed the number of classes; rebuild the engine")
+
+    def _alloc(self):
+        a, b, dev, adt = self.arch, self.batch, self.device, self.adt
+        F, N, P, D = b * a.sparse_frames, a.tokens, a.patches, a.width
+        T, Ci, Ct = a.frames, a.integration_dim, a.temporal_dim
+        Mv, Mt = F * N, b * T * P
+        z = lambda *s, dtype=adt: torch.zeros(*s, device=dev, dtype=dtype)
+        f32 = torch.float32
+        self.video = z(b, 3, T, a.resolution, a.resolution, dtype=f32)
+        self.patches_s = z(F * P, self.w.kp)
+        self.patches_d = z(b * T * P, self.w.kps)
+        self.h = z(Mv, D, dtype=f32)
+        self.ln_buf = z(Mv, D)
+        self.qkv = z(Mv, 3 * D)
+        self.attn_out = z(Mv, D)
+        self.fc1 = z(Mv, 4 * D)
+        self.tap = z(Mv, D) if self.precision == "bf16" else self.h
+        self.xT = z(Mt, Ct, dtype=f32)
+        self.xT_a = z(Mt, Ct)
+        self.xln = z(Mt, Ct)
+        self.y1 = z(Mt, a.temporal_hidden)
+        self.mid = z(Mv, Ci, dtype=f32)
+        self.mid_a = z(Mv, Ci)
+        self.res = z(Mv, Ci, dtype=f32)
+        self.int_a1 = z(Mv, Ci)
+        self.int_a2 = z(Mv, Ci)
+        self.ffn_h = z(Mv, a.integration_hidden)
+        self.tf1 = z(Mv, a.integration_temporal_hidden)
+        self.tf2 = z(Mv, a.integration_temporal_hidden)
+        self.kv_s = z(Mv, 2 * Ci)
+        self.sp = z(F, Ci, dtype=f32)
+        self.top = z(b, Ci, dtype=f32)
+        self.sp_ln, self.q_s, self.o_s, self.mlp_s = z(F, Ci), z(F, Ci), z(F, Ci), z(F, 4 * Ci)
+        self.kv_t = z(F, 2 * Ci)
+        self.top_ln, self.q_t, self.o_t, self.mlp_t = z(b, Ci), z(b, Ci), z(b, Ci), z(b, 4 * Ci)
+        self.clsmean = z(b, D)
+        self.zbuf = z(b, Ci, dtype=f32)
+        self.z_ln = z(b, Ci)
+        self.emb = z(b, a.embed_dim, dtype=f32)
+        C = self.text_n.shape[0] if self.text_n is not None else max(a.num_classes, 1)
+        self.logits = z(b, C, dtype=f32)
+        self.probs = z(b, C, dtype=f32)
+
+    # ------------------------------------------------------------------------------------------
+    def _gemm(self, *args, **kw):
+        kw.setdefault("impl", self.gemm_impl)
+        self.calls.append(ops.gemm(*args, **kw))
+
+    def _lin(self, a, w, bias, out, *, res=None, out2=None, act=ops.ACT_NONE, name="linear"):
+        """out[M, n] = act(a[M, k] @ w[n, k]^T + bias (+ res))"""
+        n, k = w.shape
+        self._gemm(a, w, n, k, bias=bias, res=res, ld_res=n, out=out, ld_out=n, out2=out2, ld_out2=n, act=act, name=name)
+
+    def _ln(self, x, gb, y, **kw):
+        self.calls.append(ops.layernorm(x, gb[0], gb[1], y, **kw))
+
+    def _plan(self):
+        a, b, w = self.arch, self.batch, self.w
+        t, T, N, P, D, g = a.sparse_frames, a.frames, a.tokens, a.patches, a.width, a.grid
+        F, Ci, Ct, al = b * t, a.integration_dim, a.temporal_dim, a.alpha
+        Mv, Mt = F * N, b * T * P
+        R = a.resolution
+        add = self.calls.append
+        bf = self.precision == "bf16"
+
+        # ---- patch rows: sparse frames for the ViT (clip.py:271 restricted to the frames kept at :281-284),
+        #      all frames for the temporal stem (dist.py:225)
+        add(ops.patchify(self.video, self.patches_s, b, T, R, R, a.patch, 0, al, t, w.kp, name="patchify.sparse"))
+        add(ops.patchify(self.video, self.patches_d, b, T, R, R, a.s_patch, 0, 1, T, w.kps, name="patchify.dense"))
+
+        # ---- ViT embedding: conv1 as GEMM, + positional embedding, class row, ln_pre (clip.py:271-276)
+        k1 = 3 * a.patch * a.patch
+        self._gemm(self.patches_s, w.conv1_w, D, k1, a_dim=(k1, P, F, 1), a_stride=(1, w.kp, P * w.kp, F * P * w.kp),
+                   groups=F, rows_per_group=P, ldb=w.kp, res=w.pos, ld_res=D, res_gstride=0, res_roff=1,
+                   out=self.h, ld_out=D, out_gstride=N, out_roff=1, name="vit.patch_embed")
+        add(ops.rows_bcast(self.h, N * D, F, D, w.cls_row, 1, False, name="vit.cls_rows"))   # class embedding + pos[0]
+        self._ln(self.h, w.ln_pre, self.h, name="vit.ln_pre")
+
+        # ---- temporal stem: Conv3d(3->Ct,(kt,ps,ps)) = kt row-shifted GEMMs over patch rows (dist.py:178-181,225)
+        ks = 3 * a.s_patch * a.s_patch
+        half = a.t_patch // 2
+        self._gemm(self.patches_d, w.stem_w, Ct, ks, a_dim=(ks, T * P, b, 1), a_stride=(1, w.kps, T * P * w.kps, b * T * P * w.kps),
+                   taps=[((k - half) * P, 0, 0) for k in range(a.t_patch)], b_tap_stride=Ct * w.kps, ldb=w.kps,
+                   groups=b, rows_per_group=T * P, bias=w.stem_b, out=self.xT, ld_out=Ct, name="dist.stem")
+
+        sel = list(a.selected_layers)
+        monotonic = all(x < y for x, y in zip(sel, sel[1:]))
+        assert monotonic, "SELECTED_LAYERS must be increasing (taps are consumed as the ViT produces them)"
+        last_sel = sel[-1]
+        for l in range(a.layers):
+            v = w.vit[l]
+            want_tap = l in sel
+            # ---- ResidualAttentionBlockMid (clip.py:170-178) ----
+            self._ln(self.h, v["ln1"], self.ln_buf, name="vit.ln_1")
+            self._lin(self.ln_buf, v["qkv_w"], v["qkv_b"], self.qkv, name="vit.qkv")
+            add(ops.attention(self.qkv, self.attn_out, F, N, a.heads, impl=self.attn_impl, name="vit.attention"))
+            self._lin(self.attn_out, v["proj_w"], v["proj_b"], self.h, res=self.h, name="vit.out_proj")
+            self._ln(self.h, v["ln2"], self.ln_buf, name="vit.ln_2")
+            self._lin(self.ln_buf, v["fc1_w"], v["fc1_b"], self.fc1, act=ops.ACT_QUICKGELU, name="vit.fc1")
+            self._lin(self.fc1, v["fc2_w"], v["fc2_b"], self.h, res=self.h,
+                      out2=self.tap if (want_tap and bf) else None, name="vit.fc2")
+            if want_tap:
+                self._plan_dist_layer(sel.index(l))
+            if l == last_sel:
+                # mean over the sparse frames of the last tapped class token (dist.py:243)
+                add(ops.mean_rows(self.h, N * D, t, b, D, self.clsmean, name="dist.cls_mean"))
+        self._plan_head()
+
+    def _plan_dist_layer(self, i):
+        a, b, w = self.arch, self.batch, self.w
+        d = w.dist[i]
+        t, T, N, P, g = a.sparse_frames, a.frames, a.tokens, a.patches, a.grid
+        F, Ci, Ct, al, Ch, Cm = b * t, a.integration_dim, a.temporal_dim, a.alpha, a.temporal_hidden, a.integration_temporal_hidden
+        Mv, Mt = F * N, b * T * P
+        add = self.calls.append
+        half = a.t_kernel // 2
+
+        # ---- TemporalNet (dist.py:48-65) ----
+        self._ln(self.xT, d["tn_ln"], self.xln, name="dist.tn.ln")
+        self._gemm(self.xln, d["tn_w1"], Ch, Ct, a_dim=(Ct, T * P, b, 1), a_stride=(1, Ct, T * P * Ct, Mt * Ct),
+                   taps=[((k - half) * P, 0, 0) for k in range(a.t_kernel)], b_tap_stride=Ch * Ct, ldb=Ct,
+                   groups=b, rows_per_group=T * P, bias=d["tn_b1"], out=self.y1, ld_out=Ch, act=ops.ACT_QUICKGELU,
+                   name="dist.tn.conv_t")
+        self._gemm(self.y1, d["tn_w2"], Ct, Ch, a_dim=(Ch, g, g, b * T), a_stride=(1, Ch, g * Ch, P * Ch), img_w=g,
+                   taps=[(j - 1, ii - 1, 0) for ii in range(3) for j in range(3)], b_tap_stride=Ct * Ch, ldb=Ch,
+                   groups=b * T, rows_per_group=P, bias=d["tn_b2"], res=self.xT, ld_res=Ct, res_gstride=P,
+                   out=self.xT, ld_out=Ct, out2=self.xT_a, ld_out2=Ct, act=ops.ACT_QUICKGELU, name="dist.tn.conv_s")
+
+        # ---- input linear + previous integration output (dist.py:229) ----
+        self._lin(self.tap, d["in_w"], d["in_b"], self.mid, res=self.res if i > 0 else None, out2=self.mid_a, name="dist.input_linear")
+
+        # ---- temporal -> integration (dist.py:68-86,232): alpha-tap GEMM over frame groups, result added onto the patch rows
+        self._gemm(self.xT_a, d["t2i_w"], Ci, Ct, a_dim=(Ct, P, al, F), a_stride=(1, Ct, P * Ct, al * P * Ct), group_dim=3,
+                   taps=[(0, k, 0) for k in range(al)], b_tap_stride=Ci * Ct, ldb=Ct, groups=F, rows_per_group=P,
+                   bias=d["t2i_b"], res=self.mid, ld_res=Ci, res_gstride=N, res_roff=1,
+                   out=self.mid, ld_out=Ci, out_gstride=N, out_roff=1, name="dist.t2i")
+        add(ops.rows_bcast(self.mid, N * Ci, F, Ci, d["t2i_cls"], t, True, name="dist.t2i.cls"))
+
+        # ---- integration -> temporal (dist.py:90-105,231): patch tokens only, nearest upsample = row replication
+        self._gemm(self.mid_a, d["i2t_w"], Ct, Ci, a_dim=(Ci, N, F, 1), a_stride=(1, Ci, N * Ci, Mv * Ci), taps=[(1, 0, 0)],
+                   groups=F, rows_per_group=P, ldb=Ci, bias=d["i2t_b"], res=self.xT, ld_res=Ct, res_gstride=al * P,
+                   res_rep_stride=P, out=self.xT, ld_out=Ct, out_gstride=al * P, out_rep=al, out_rep_stride=P, name="dist.i2t")
+
+        # ---- IntegrationNetwork (dist.py:16-45) on upd = mid ----
+        add(ops.layernorm(self.mid, d["ln"][0], d["ln"][1], self.int_a1, g2=d["ln_t"][0], b2=d["ln_t"][1], y2=self.int_a2,
+                          name="dist.int.ln"))
+        self._lin(self.int_a1, d["fc_w"], d["fc_b"], self.ffn_h, act=ops.ACT_QUICKGELU, name="dist.int.ffn_fc")
+        self._lin(self.ffn_h, d["pr_w"], d["pr_b"], self.res, name="dist.int.ffn_proj")
+        self._lin(self.int_a2, d["tf1_w"], d["tf1_b"], self.tf1, name="dist.int.t_fc1")
+        self._gemm(self.tf1, d["tf2_w"], Cm, Cm, a_dim=(Cm, t * N, b, 1), a_stride=(1, Cm, t * N * Cm, Mv * Cm),
+                   taps=[((k - half) * N, 0, 0) for k in range(a.t_kernel)], b_tap_stride=Cm * Cm, ldb=Cm,
+                   groups=b, rows_per_group=t * N, bias=d["tf2_b"], out=self.tf2, ld_out=Cm, act=ops.ACT_QUICKGELU,
+                   name="dist.int.t_conv")
+        self._lin(self.tf2, d["tf3_w"], d["tf3_b"], self.res, res=self.res, name="dist.int.t_proj")
+
+    def _plan_head(self):
+        a, b, w = self.arch, self.batch, self.w
+        t, N, Ci = a.sparse_frames, a.tokens, a.integration_dim
+        F, Mv, H = b * t, b * t * N, a.integration_heads
+        add = self.calls.append
+        # ---- ada-pooling (dist.py:237-241, 139-162) ----
+        add(ops.rows_bcast(self.sp, Ci, F, Ci, w.agg_sp, 1, False, name="ada.init_sp"))
+        add(ops.rows_bcast(self.top, Ci, b, Ci, w.agg_cls, 1, False, name="ada.init_top"))
+        for j in range(a.ada_layers):
+            e = w.ada[j]
+            s, tp = e["sp"], e["tp"]
+            # spatial: query = per-frame token, key = value = LN(res + upd)  (clip.py:146-147)
+            self._ln(self.res, s["ln"], self.int_a1, in2=self.mid, in2_period=Mv, name="ada.sp.ln_kv")
+            self._lin(self.int_a1, s["kv_w"], s["kv_b"], self.kv_s, name="ada.sp.kv")
+            self._ln(self.sp, s["ln"], self.sp_ln, name="ada.sp.ln_q")
+            self._lin(self.sp_ln, s["q_w"], s["q_b"], self.q_s, name="ada.sp.q")
+            add(ops.cross_attention(self.q_s, self.kv_s, self.o_s, F, N, H, name="ada.sp.attn"))
+            self._lin(self.o_s, s["o_w"], s["o_b"], self.sp, res=self.sp, name="ada.sp.out_proj")
+            self._ln(self.sp, s["ln_out"], self.sp_ln, name="ada.sp.ln_out")
+            self._lin(self.sp_ln, s["fc_w"], s["fc_b"], self.mlp_s, act=ops.ACT_QUICKGELU, name="ada.sp.fc")
+            self._lin(self.mlp_s, s["pr_w"], s["pr_b"], self.sp, res=self.sp, name="ada.sp.proj")
+            # temporal: query = clip token, keys = the t frame tokens + positional embedding (dist.py:155-160)
+            self._ln(self.sp, tp["ln"], self.sp_ln, in2=e["pos"], in2_period=t, name="ada.tp.ln_kv")
+            self._lin(self.sp_ln, tp["kv_w"], tp["kv_b"], self.kv_t, name="ada.tp.kv")
+            self._ln(self.top, tp["ln"], self.top_ln, name="ada.tp.ln_q")
+            self._lin(self.top_ln, tp["q_w"], tp["q_b"], self.q_t, name="ada.tp.q")
+            add(ops.cross_attention(self.q_t, self.kv_t, self.o_t, b, t, H, name="ada.tp.attn"))
+            self._lin(self.o_t, tp["o_w"], tp["o_b"], self.top, res=self.top, name="ada.tp.out_proj")
+            self._ln(self.top, tp["ln_out"], self.top_ln, name="ada.tp.ln_out")
+            self._lin(self.top_ln, tp["fc_w"], tp["fc_b"], self.mlp_t, act=ops.ACT_QUICKGELU, name="ada.tp.fc")
+            self._lin(self.mlp_t, tp["pr_w"], tp["pr_b"], self.top, res=self.top, name="ada.tp.proj")
+        # ---- tail (dist.py:242-246) ----
+        self._lin(self.clsmean, w.pcls_w, w.pcls_b, self.zbuf, res=self.top, name="tail.proj_spatial_cls")
+        self._ln(self.zbuf, w.ln_post, self.z_ln, name="tail.ln_post")
+        self._lin(self.z_ln, w.proj_w, None, self.emb, name="tail.proj")
+        self.head_call = None
+        if self.text_n is not None:
+            # clip.py:511-518 + base_blocks.py:579-585
+            self.head_call = ops.class_head(self.emb, self.text_n, w.logit_scale, b, a.embed_dim, self.text_n.shape[0],
+                                            self.logits, self.probs, name="head.class_scores")
+            add(self.head_call)
+
+    # ------------------------------------------------------------------------------------------
+    @property
+    def num_launches(self):
+        # patchify issues a second (padding) kernel when the patch row is padded
+        extra = sum(1 for c in self.calls if c.name.startswith("patchify") and c.args[10] > 3 * c.args[6] * c.args[6])
+        return len(self.calls) + extra
+
+    def run(self, stream=None):
+        """Replay the planned forward on ``stream`` (default: torch's current stream)."""
+        s = (stream or torch.cuda.current_stream(self.device)).cuda_stream
+        for c in self.calls:
+            c.launch(s)
+
+    def capture(self):
+        """Capture the plan into a CUDA graph (all buffers are static)."""
+        side = torch.cuda.Stream(self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            self.run(side)          # warm-up outside capture (function attributes, module load)
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            self.run(torch.cuda.current_stream(self.device))
+        self.graph = graph
+        return graph
+
+    def forward(self, video=None, use_graph=True):
+        """video [b, 3, T, H, W] fp32 (host or device) -> embedding [b, E] fp32 (view of an internal buffer)."""
+        if video is not None:
+            assert tuple(video.shape) == tuple(self.video.shape), (video.shape, self.video.shape)
+            self.video.copy_(video, non_blocking=True)
+        if use_graph and self.graph is not None:
+            self.graph.replay()
+        else:
+            self.run()
+        return self.emb
+
+    def flops(self):
+        return sum(c.flops for c in self.calls)

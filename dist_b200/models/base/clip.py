@@ -1,0 +1,223 @@
+"""CLIP vision tower + DiST wiring on the distb200 CUDA path (reference: ``models/base/clip.py``).
+
+The modules below own parameters under exactly the reference's ``state_dict`` names
+(SURVEY.md section 8b), so reference checkpoints load unchanged; their arithmetic runs in
+``dist_b200.engine.DistEngine`` through the C ABI - torch layers such as ``nn.Linear`` or
+``nn.MultiheadAttention`` appear here only as parameter containers and are never called.
+The text tower is outside this path: label embeddings enter as a constant ``[C, E]`` matrix
+(``set_text_features`` / ``others['label_embeddings']``, cf. ``clip.py:437-439``).
+"""
+
+from collections import OrderedDict
+import math
+import os
+
+import numpy as np
+import torch
+from torch import nn
+
+from ...arch import arch_from_cfg
+from ...registry import Registry
+from ...utils import synth
+
+TEMPORALNET_REGISTRY = Registry("TemporalNet")
+ATTEN_BLOCK_REGISTRY = Registry("AttentionBlock")
+
+
+class LayerNorm(nn.LayerNorm):
+    """Parameter holder; statistics are always fp32 on the CUDA path (``clip.py:181-187``)."""
+
+
+class QuickGELU(nn.Module):
+    """x * sigmoid(1.702 x) - fused into GEMM epilogues (``clip.py:199-201``)."""
+
+    def forward(self, x):
+        raise RuntimeError("QuickGELU is fused into the distb200 GEMM epilogue; it is not called as a module")
+
+
+class CrossAttentionBlockGenral(nn.Module):
+    """Single-query cross attention block of the ada-pooling head (``clip.py:139-147``)."""
+
+    def __init__(self, d_model, n_head, attn_mask=None, cfg=None, layer_id=0):
+        super().__init__()
+        self.layer_id = layer_id
+        self.attn = nn.MultiheadAttention(d_model, n_head)
+        self.ln_1 = LayerNorm(d_model)
+
+
+@ATTEN_BLOCK_REGISTRY.register()
+class ResidualAttentionBlockMid(nn.Module):
+    """ViT block whose output is tapped for DiST (``clip.py:150-178``).
+
+    Block protocol of the reference: ctor ``(d_model, n_head, attn_mask, cfg=, layer_id=)``; inside the fused
+    engine the tap ``others["mid_feat"]["img"][layer_id]`` is the bf16 copy the FC2 epilogue writes.
+    """
+
+    def __init__(self, d_model, n_head, attn_mask=None, cfg=None, layer_id=0):
+        super().__init__()
+        assert attn_mask is None, "the image transformer runs without a mask"
+        self.layer_id = layer_id
+        self.attn = nn.MultiheadAttention(d_model, n_head)
+        self.ln_1 = LayerNorm(d_model)
+        self.mlp = nn.Sequential(OrderedDict([
+            ("c_fc", nn.Linear(d_model, d_model * 4)),
+            ("gelu", QuickGELU()),
+            ("c_proj", nn.Linear(d_model * 4, d_model)),
+        ]))
+        self.ln_2 = LayerNorm(d_model)
+        self.attn_mask = None
+        self.is_image_transformer = True
+
+
+class Transformer(nn.Module):
+    def __init__(self, width, layers, heads, attn_mask=None, cfg=None):
+        super().__init__()
+        self.width, self.layers = width, layers
+        name = cfg.VIDEO.BACKBONE.ATTEN_BLOCK if cfg is not None else "ResidualAttentionBlockMid"
+        block = ATTEN_BLOCK_REGISTRY.get(name)
+        if block is None:
+            raise KeyError("attention block {!r} is not registered (the DiST configs select ResidualAttentionBlockMid)".format(name))
+        self.resblocks = nn.Sequential(*[block(width, heads, attn_mask, cfg=cfg, layer_id=i) for i in range(layers)])
+
+
+class VisionTransformer(nn.Module):
+    """CLIP ViT parameters (``clip.py:218-261``)."""
+
+    def __init__(self, cfg, input_resolution, patch_size, width, layers, heads, output_dim):
+        super().__init__()
+        self.cfg = cfg
+        self.input_resolution, self.output_dim = input_resolution, output_dim
+        self.num_frames = cfg.DATA.NUM_INPUT_FRAMES
+        self.sparse_sample_alpha = getattr(cfg.DATA, "SPARSE_SAMPLE_ALPHA", 1)
+        self.conv1 = nn.Conv2d(3, width, kernel_size=patch_size, stride=patch_size, bias=False)
+        scale = width ** -0.5
+        self.class_embedding = nn.Parameter(scale * torch.randn(width))
+        self.positional_embedding = nn.Parameter(scale * torch.randn((input_resolution // patch_size) ** 2 + 1, width))
+        self.ln_pre = LayerNorm(width)
+        self.transformer = Transformer(width, layers, heads, cfg=cfg)
+        self.ln_post = LayerNorm(width)
+        self.proj = nn.Parameter(scale * torch.randn(width, output_dim))
+
+
+class CLIP(nn.Module):
+    """``visual`` + ``dist_net`` + ``logit_scale``; forwards run the planned CUDA path."""
+
+    def __init__(self, cfg, embed_dim, image_resolution, vision_layers, vision_width, vision_patch_size, arch=None):
+        super().__init__()
+        from ..module_zoo.branches.dist import DiSTNetwork
+        self.cfg = cfg
+        self.num_frames = cfg.DATA.NUM_INPUT_FRAMES
+        self.freeze_text = cfg.VIDEO.BACKBONE.FREEZE_TEXT
+        self.freeze_visual = getattr(cfg.VIDEO.BACKBONE, "FREEZE_VISUAL", True)
+        self.num_classes = cfg.VIDEO.HEAD.NUM_CLASSES
+        self.visual = VisionTransformer(cfg, image_resolution, vision_patch_size, vision_width, vision_layers,
+                                        vision_width // 64, embed_dim)
+        self.dist_net = DiSTNetwork(cfg, d_model=vision_width, width=vision_width, output_dim=embed_dim)
+        self.logit_scale = nn.Parameter(torch.ones([]) * np.log(1 / 0.07))
+        self.arch = arch
+        b200 = getattr(cfg, "B200", None)
+        self.precision = getattr(b200, "PRECISION", "bf16") if b200 is not None else "bf16"
+        self.use_graph = bool(getattr(b200, "CUDA_GRAPH", True)) if b200 is not None else True
+        self.text_features = None
+        self._engines = {}
+
+    # ---- label embeddings ---------------------------------------------------------------------
+    def set_text_features(self, feats):
+        self.text_features = feats.detach().float()
+        self._engines.clear()
+
+    def _text_from(self, text, others):
+        if others is not None and "label_embeddings" in others:            # clip.py:437-439
+            return others["label_embeddings"]
+        if text is not None and torch.is_floating_point(text):
+            return text
+        if self.text_features is not None:
+            return self.text_features
+        raise NotImplementedError(
+            "token ids were passed but no label embeddings are cached; the CLIP text tower is outside the DiST "
+            "forward path (SURVEY.md section 8f) - call set_text_features([C, E]) with embeddings computed once")
+
+    # ---- engine cache -------------------------------------------------------------------------
+    def _engine(self, batch, device, text):
+        from ...engine import DistEngine
+        version = sum(p._version for p in self.parameters())
+        tkey = None if text is None else (text.data_ptr(), tuple(text.shape), text._version)
+        key = (batch, str(device), self.precision)
+        hit = self._engines.get(key)
+        if hit is not None and hit[1] == version and hit[2] == tkey:
+            return hit[0]
+        sd = {k: v for k, v in self.state_dict().items()}
+        eng = DistEngine(sd, self.arch, batch, device=device, precision=self.precision, text_features=text)
+        if self.use_graph:
+            eng.capture()
+        self._engines[key] = (eng, version, tkey)
+        return eng
+
+    def refresh_engine(self):
+        self._engines.clear()
+
+    # ---- forwards (clip.py:460-533) -------------------------------------------------------------
+    def forward(self, image, text, others=None):
+        if text is not None or (others is not None and "label_embeddings" in others):
+            return self.forward_with_text(image, text, others)
+        return self.forward_without_text(image)
+
+    def _as_clips(self, image):
+        """Accept the reference's frame-major ``[B*T,3,H,W]`` (clip.py:460) or the native ``[B,3,T,H,W]``."""
+        if image.dim() == 4:
+            bt, c, h, w = image.shape
+            image = image.view(bt // self.num_frames, self.num_frames, c, h, w).permute(0, 2, 1, 3, 4).contiguous()
+        return image
+
+    def forward_without_text(self, image):
+        if not image.is_cuda:
+            raise RuntimeError("dist_b200 runs on a CUDA device only; there is no CPU path")
+        clips = self._as_clips(image)
+        eng = self._engine(clips.shape[0], clips.device, None)
+        emb = eng.forward(clips.float(), use_graph=self.use_graph)
+        return emb.clone()[:, None, :]                                       # clip.py:480
+
+    def forward_with_text(self, image, text, others=None):
+        if not image.is_cuda:
+            raise RuntimeError("dist_b200 runs on a CUDA device only; there is no CPU path")
+        clips = self._as_clips(image)
+        feats = self._text_from(text, others)
+        eng = self._engine(clips.shape[0], clips.device, feats)
+        emb = eng.forward(clips.float(), use_graph=self.use_graph)
+        logits = eng.logits.clone()
+        vid = emb / emb.norm(dim=1, keepdim=True)                           # clip.py:513 (returned, not on the scored path)
+        return {"logits_per_image": logits, "logits_per_text": logits.t(), "probs_per_image": eng.probs.clone(),
+                "img_logits": None, "vid_logits": vid[:, None, :]}
+
+
+def build_model(cfg, state_dict):
+    """Infer the geometry from the checkpoint like ``clip.py:564-611`` and load it (``strict=False``)."""
+    arch = arch_from_cfg(cfg, state_dict)
+    model = CLIP(cfg, arch.embed_dim, arch.resolution, arch.layers, arch.width, arch.patch, arch=arch)
+    own = model.state_dict()
+    usable = {k: v for k, v in state_dict.items() if k in own and own[k].shape == v.shape}
+    missing = sorted(set(own) - set(usable))
+    model.load_state_dict(usable, strict=False)
+    model.missing_keys = missing
+    return model.eval()
+
+
+def load(cfg):
+    """``clip.load`` (``clip.py:614-629``): a TorchScript CLIP archive or a ``.pyth`` state_dict; random init when no path is set."""
+    bb = cfg.VIDEO.BACKBONE
+    path = getattr(bb, "PRETRAIN_WEIGHT_PATH", "") or ""
+    local = getattr(bb, "LOCAL_PRETRAIN_WEIGHT_PATH", "") or ""
+    if local and os.path.exists(local):
+        path = local
+    if path and os.path.exists(path):
+        if path.endswith(".pyth") or path.endswith(".pth"):
+            state_dict = torch.load(path, map_location="cpu")
+            if "model_state" in state_dict:
+                state_dict = {k.replace("backbone.base_encoder.", ""): v for k, v in state_dict["model_state"].items()}
+        else:
+            state_dict = torch.jit.load(path, map_location="cpu").state_dict()
+        return build_model(cfg, state_dict)
+    # "random initialization, only for debugging" (utils/checkpoint.py:524-527)
+    arch = arch_from_cfg(cfg)
+    seed = int(getattr(cfg, "RANDOM_SEED", 0))
+    return build_model(cfg, synth.synth_state_dict(arch, seed=seed, init="reference"))

@@ -1,0 +1,230 @@
+"""ctypes binding of ``libdistb200.so`` (the C ABI declared in ``include/distb200.h``).
+
+There is deliberately no fallback: if the shared library is missing or fails to load, importing
+:func:`lib` raises.  Every wrapper here turns torch tensors into raw pointers / sizes and returns a
+*prepared call* - a ``(c_function, argument tuple)`` pair - so that the engine can build the whole
+forward once and replay it with negligible host work (and capture it into a CUDA graph).
+"""
+
+import ctypes as C
+import os
+
+import torch
+
+from . import build as _build
+
+F32, BF16 = 0, 1
+ACT_NONE, ACT_QUICKGELU = 0, 1
+IMPL_AUTO, IMPL_SIMT, IMPL_TCGEN05 = 0, 1, 2
+MAX_TAPS = 9
+
+_TORCH2ENUM = {torch.float32: F32, torch.bfloat16: BF16}
+
+
+class GemmDesc(C.Structure):
+    """Mirror of ``distb200_gemm_desc`` (field order and types must match the header)."""
+    _fields_ = [
+        ("a", C.c_void_p), ("b", C.c_void_p),
+        ("dtype", C.c_int32), ("impl", C.c_int32),
+        ("a_dim", C.c_int64 * 4), ("a_stride", C.c_int64 * 4),
+        ("img_w", C.c_int32), ("num_taps", C.c_int32),
+        ("tap_off", (C.c_int32 * 3) * MAX_TAPS),
+        ("ldb", C.c_int64), ("b_tap_stride", C.c_int64),
+        ("n", C.c_int32), ("k", C.c_int32),
+        ("groups", C.c_int64), ("rows_per_group", C.c_int64),
+        ("bias", C.c_void_p), ("res", C.c_void_p),
+        ("ld_res", C.c_int64), ("res_gstride", C.c_int64), ("res_roff", C.c_int64), ("res_rep_stride", C.c_int64),
+        ("out", C.c_void_p), ("out_dtype", C.c_int32), ("out_rep", C.c_int32),
+        ("ld_out", C.c_int64), ("out_gstride", C.c_int64), ("out_roff", C.c_int64), ("out_rep_stride", C.c_int64),
+        ("out2", C.c_void_p), ("out2_dtype", C.c_int32), ("act", C.c_int32),
+        ("ld_out2", C.c_int64), ("block_n", C.c_int32), ("group_dim", C.c_int32),
+    ]
+
+
+_LIB = None
+
+
+def lib():
+    """Load the CUDA library, building it first when the sources are newer (needs nvcc)."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = _build.LIB
+    if _build.is_stale():
+        try:
+            _build.build()
+        except Exception as exc:  # no nvcc on the box and no prebuilt library
+            if not os.path.exists(path):
+                raise RuntimeError(
+                    "dist_b200: the CUDA extension {} is missing and could not be built ({}). There is no "
+                    "CPU or PyTorch fallback for this path.".format(path, exc)) from exc
+    try:
+        L = C.CDLL(path)
+    except OSError as exc:
+        raise RuntimeError("dist_b200: cannot load {}: {} (no fallback exists)".format(path, exc)) from exc
+    i32, i64, f32, vp = C.c_int32, C.c_int64, C.c_float, C.c_void_p
+    L.distb200_version.restype = C.c_int
+    L.distb200_arch.restype = C.c_int
+    L.distb200_last_error.restype = C.c_char_p
+    L.distb200_gemm.argtypes = [C.POINTER(GemmDesc), vp]
+    L.distb200_layernorm.argtypes = [vp, i64, vp, i64, i64, i64, i32, f32, vp, vp, vp, i64, vp, vp, vp, i64, i32, vp]
+    L.distb200_attention.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp]
+    L.distb200_cross_attention.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp]
+    L.distb200_patchify.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i64, i32, vp]
+    L.distb200_rows_bcast.argtypes = [vp, i64, i64, i32, vp, i64, i32, vp]
+    L.distb200_mean_rows.argtypes = [vp, i64, i32, i64, i32, vp, i32, vp]
+    L.distb200_class_head.argtypes = [vp, vp, f32, i32, i32, i32, vp, vp, vp]
+    for name in ("gemm", "layernorm", "attention", "cross_attention", "patchify", "rows_bcast", "mean_rows", "class_head"):
+        getattr(L, "distb200_" + name).restype = C.c_int
+    assert L.distb200_version() == 100 and L.distb200_arch() == 100
+    _LIB = L
+    return L
+
+
+EXPORTS = ("distb200_version", "distb200_arch", "distb200_last_error", "distb200_gemm", "distb200_layernorm",
+           "distb200_attention", "distb200_cross_attention", "distb200_patchify", "distb200_rows_bcast",
+           "distb200_mean_rows", "distb200_class_head")
+
+
+class DistB200Error(RuntimeError):
+    pass
+
+
+def _check(code, what):
+    if code != 0:
+        raise DistB200Error("{} failed ({}): {}".format(what, code, lib().distb200_last_error().decode()))
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def enum_of(t):
+    return _TORCH2ENUM[t.dtype]
+
+
+class Call:
+    """A prepared C call: ``launch(stream_ptr)`` runs it on the given CUDA stream."""
+    __slots__ = ("fn", "args", "name", "keep", "flops", "bytes")
+
+    def __init__(self, fn, args, name, keep=(), flops=0, nbytes=0):
+        self.fn, self.args, self.name, self.keep, self.flops, self.bytes = fn, args, name, keep, flops, nbytes
+
+    def launch(self, stream):
+        code = self.fn(*self.args, stream)
+        if code != 0:
+            _check(code, self.name)
+
+
+def gemm(a, b, n, k, *, a_dim=None, a_stride=None, taps=((0, 0, 0),), b_tap_stride=0, ldb=None, img_w=0,
+         groups=1, rows_per_group=None, group_dim=2, bias=None, res=None, ld_res=0, res_gstride=0, res_roff=0,
+         res_rep_stride=0, out=None, ld_out=0, out_gstride=None, out_roff=0, out_rep=1, out_rep_stride=0,
+         out2=None, ld_out2=0, act=ACT_NONE, impl=IMPL_AUTO, block_n=0, name="gemm"):
+    """Prepare one ``distb200_gemm`` (see the header for the exact definition).
+
+    Defaults describe a plain ``out[M, n] = a[M, k] @ b[n, k]^T``: ``a`` is a 2-D row-major tensor,
+    one group of ``M`` rows.  ``a_dim`` / ``a_stride`` override the logical A tensor (elements).
+    """
+    d = GemmDesc()
+    d.a, d.b = a.data_ptr(), b.data_ptr()
+    assert a.dtype == b.dtype, (a.dtype, b.dtype)
+    d.dtype, d.impl = enum_of(a), impl
+    if a_dim is None:
+        assert a.dim() == 2 and a.stride(1) == 1
+        a_dim = (k, a.shape[0], 1, 1)
+        a_stride = (1, a.stride(0), a.stride(0) * a.shape[0], a.stride(0) * a.shape[0])
+        if rows_per_group is None:
+            rows_per_group = a.shape[0]
+    for i in range(4):
+        d.a_dim[i], d.a_stride[i] = int(a_dim[i]), int(a_stride[i])
+    d.img_w, d.num_taps = int(img_w), len(taps)
+    assert 1 <= len(taps) <= MAX_TAPS
+    for j, tp in enumerate(taps):
+        for i in range(3):
+            d.tap_off[j][i] = int(tp[i])
+    d.ldb = int(ldb if ldb is not None else b.stride(-2))
+    d.b_tap_stride = int(b_tap_stride)
+    d.n, d.k = int(n), int(k)
+    d.groups, d.rows_per_group, d.group_dim = int(groups), int(rows_per_group), int(group_dim)
+    d.bias, d.res = _ptr(bias), _ptr(res)
+    if bias is not None:
+        assert bias.dtype == torch.float32
+    if res is not None:
+        assert res.dtype == torch.float32
+    d.ld_res, d.res_gstride, d.res_roff, d.res_rep_stride = int(ld_res), int(res_gstride), int(res_roff), int(res_rep_stride)
+    d.out = _ptr(out)
+    d.out_dtype = enum_of(out) if out is not None else F32
+    d.out_rep = int(out_rep)
+    d.ld_out = int(ld_out)
+    d.out_gstride = int(out_gstride if out_gstride is not None else rows_per_group)
+    d.out_roff, d.out_rep_stride = int(out_roff), int(out_rep_stride)
+    d.out2 = _ptr(out2)
+    d.out2_dtype = enum_of(out2) if out2 is not None else F32
+    d.act, d.ld_out2, d.block_n = int(act), int(ld_out2), int(block_n)
+    rows = int(groups) * int(rows_per_group)
+    flops = 2 * rows * int(n) * int(k) * len(taps)
+    esz = a.element_size()
+    nbytes = rows * int(k) * esz + int(n) * int(k) * len(taps) * esz
+    if out is not None:
+        nbytes += rows * int(n) * out.element_size() * int(out_rep)
+    if out2 is not None:
+        nbytes += rows * int(n) * out2.element_size() * int(out_rep)
+    if res is not None:
+        nbytes += rows * int(n) * 4 * int(out_rep)
+    return Call(lib().distb200_gemm, (C.byref(d),), name, keep=(d, a, b, bias, res, out, out2), flops=flops, nbytes=nbytes)
+
+
+def layernorm(x, g1, b1, y1, *, in2=None, in2_period=1, g2=None, b2=None, y2=None, rows=None, cols=None,
+              ld_in1=None, ld_in2=None, ld_y1=None, ld_y2=None, eps=1e-5, name="layernorm"):
+    assert x.dtype == torch.float32
+    cols = int(cols if cols is not None else x.shape[-1])
+    rows = int(rows if rows is not None else x.numel() // cols)
+    ld_in1 = int(ld_in1 if ld_in1 is not None else cols)
+    ld_y1 = int(ld_y1 if ld_y1 is not None else cols)
+    if y2 is not None:
+        assert y2.dtype == y1.dtype
+    args = (x.data_ptr(), ld_in1, _ptr(in2), int(ld_in2 if ld_in2 is not None else cols), int(in2_period), rows, cols,
+            float(eps), g1.data_ptr(), b1.data_ptr(), y1.data_ptr(), ld_y1, _ptr(g2), _ptr(b2), _ptr(y2),
+            int(ld_y2 if ld_y2 is not None else cols), enum_of(y1))
+    nbytes = rows * cols * (4 + (4 if in2 is not None else 0) + y1.element_size() * (2 if y2 is not None else 1))
+    return Call(lib().distb200_layernorm, args, name, keep=(x, in2, g1, b1, y1, g2, b2, y2), nbytes=nbytes)
+
+
+def attention(qkv, out, frames, tokens, heads, impl=IMPL_AUTO, name="attention"):
+    assert qkv.dtype == out.dtype
+    args = (qkv.data_ptr(), out.data_ptr(), int(frames), int(tokens), int(heads), enum_of(qkv), int(impl))
+    flops = 4 * frames * heads * tokens * tokens * 64
+    nbytes = frames * tokens * heads * 64 * 4 * qkv.element_size()
+    return Call(lib().distb200_attention, args, name, keep=(qkv, out), flops=flops, nbytes=nbytes)
+
+
+def cross_attention(q, kv, out, batch, keys, heads, name="cross_attention"):
+    assert q.dtype == kv.dtype == out.dtype
+    args = (q.data_ptr(), kv.data_ptr(), out.data_ptr(), int(batch), int(keys), int(heads), enum_of(q))
+    return Call(lib().distb200_cross_attention, args, name, keep=(q, kv, out),
+                flops=4 * batch * keys * heads * 64, nbytes=batch * keys * heads * 128 * q.element_size())
+
+
+def patchify(video, out, clips, T, H, W, p, first, step, n_sel, ld_out, name="patchify"):
+    assert video.dtype == torch.float32 and video.is_contiguous()
+    args = (video.data_ptr(), out.data_ptr(), int(clips), int(T), int(H), int(W), int(p), int(first), int(step), int(n_sel),
+            int(ld_out), enum_of(out))
+    px = clips * n_sel * 3 * H * W
+    return Call(lib().distb200_patchify, args, name, keep=(video, out), nbytes=px * (4 + out.element_size()))
+
+
+def rows_bcast(dst, row_stride, n_rows, cols, table, period, accumulate, name="rows_bcast"):
+    assert dst.dtype == torch.float32 and table.dtype == torch.float32
+    args = (dst.data_ptr(), int(row_stride), int(n_rows), int(cols), table.data_ptr(), int(period), int(bool(accumulate)))
+    return Call(lib().distb200_rows_bcast, args, name, keep=(dst, table), nbytes=n_rows * cols * 8)
+
+
+def mean_rows(src, row_stride, count, batch, cols, out, name="mean_rows"):
+    assert src.dtype == torch.float32
+    args = (src.data_ptr(), int(row_stride), int(count), int(batch), int(cols), out.data_ptr(), enum_of(out))
+    return Call(lib().distb200_mean_rows, args, name, keep=(src, out), nbytes=batch * cols * (4 * count + out.element_size()))
+
+
+def class_head(emb, text_n, scale, batch, embed_dim, classes, logits, probs, name="class_head"):
+    args = (emb.data_ptr(), text_n.data_ptr(), float(scale), int(batch), int(embed_dim), int(classes), _ptr(logits), _ptr(probs))
+    return Call(lib().distb200_class_head, args, name, keep=(emb, text_n, logits, probs))

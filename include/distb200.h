@@ -53,7 +53,7 @@ const char* distb200_last_error(void);
  * Definition.  Output rows are indexed by (group gi in [0,groups), row r in [0,rows_per_group)).
  * A is a logical 4-D tensor with element (c0,c1,c2,c3) at a + sum(ci * a_stride[i]), a_stride[0] == 1,
  * reading as zero outside [0,a_dim[i]).  For tap j with offsets (d1,d2,d3) = tap_off[j]:
- *     img_w == 0 :  A_j(gi,r,k) = A[k, r + d1,        gi + d2,         d3]
+ *     img_w == 0 :  A_j(gi,r,k) = A[k, r + d1, d2 (+ gi if group_dim == 2), d3 (+ gi if group_dim == 3)]
  *     img_w  > 0 :  A_j(gi,r,k) = A[k, r % img_w + d1, r / img_w + d2, gi + d3]
  *     acc(gi,r,n) = sum_j sum_k A_j(gi,r,k) * B[j*b_tap_stride + n*ldb + k]
  *     v           = acc + bias[n] + res[res_row(gi,r,rep)*ld_res + n]      (each term optional)
@@ -96,7 +96,7 @@ typedef struct distb200_gemm_desc {
     int32_t act;
     int64_t ld_out2;
     int32_t block_n;               /* tcgen05 N tile, 0 = choose */
-    int32_t reserved;
+    int32_t group_dim;             /* 2 (default when 0) or 3: which A coordinate the group index adds to */
 } distb200_gemm_desc;
 
 int distb200_gemm(const distb200_gemm_desc* desc, void* stream);

@@ -1,0 +1,48 @@
+"""Shared helpers for the parity tests: rebuild the synthetic inputs a fixture was generated from."""
+import torch
+
+from dist_b200.arch import DistArch
+from dist_b200.utils import synth
+
+
+def inputs_for(fix):
+    arch = DistArch(**fix["arch"]).validate()
+    sd = synth.synth_state_dict(arch, seed=fix["weight_seed"], init=fix["init"])
+    clips = synth.synth_clips(fix["batch"], arch, seed=fix["clip_seed"], kind=fix["clip_kind"])
+    text = synth.synth_text_features(arch.num_classes, arch.embed_dim, seed=fix["text_seed"])
+    return arch, sd, clips, text
+
+
+def check_inputs(fix, sd, clips, text, rtol=1e-6):
+    """The seeded generators must reproduce the tensors the reference was run on."""
+    def close(a, b):
+        return all(abs(x - y) <= rtol * max(1.0, abs(y)) for x, y in zip(a, b))
+    assert close(synth.checksum({k: v for k, v in sd.items() if k != "logit_scale"}), fix["weights_checksum"]), "synthetic weights differ from the fixture's"
+    assert close(synth.checksum(clips), fix["clips_checksum"]), "synthetic clips differ from the fixture's"
+    assert close(synth.checksum(text), fix["text_checksum"]), "synthetic label embeddings differ from the fixture's"
+
+
+def gemm_reference(a4, a_dim, taps, b3, groups, rpg, img_w=0, group_dim=2):
+    """fp64 restatement of the operand addressing in include/distb200.h.
+
+    a4: logical A tensor indexed [c3, c2, c1, k] (a torch tensor of shape a_dim reversed);
+    b3: [taps, n, k].  Returns acc [groups*rpg, n]."""
+    K = a_dim[0]
+    dev = a4.device
+    gi = torch.arange(groups, device=dev).repeat_interleave(rpg)
+    r = torch.arange(rpg, device=dev).repeat(groups)
+    acc = torch.zeros(groups * rpg, b3.shape[1], dtype=torch.float64, device=dev)
+    for j, (d1, d2, d3) in enumerate(taps):
+        if img_w > 0:
+            c1, c2, c3 = r % img_w + d1, r // img_w + d2, gi + d3
+        else:
+            c1 = r + d1
+            c2 = d2 + (gi if group_dim == 2 else 0)
+            c3 = d3 + (gi if group_dim == 3 else 0)
+            c2 = c2 if torch.is_tensor(c2) else torch.full_like(r, c2)
+            c3 = c3 if torch.is_tensor(c3) else torch.full_like(r, c3)
+        ok = (c1 >= 0) & (c1 < a_dim[1]) & (c2 >= 0) & (c2 < a_dim[2]) & (c3 >= 0) & (c3 < a_dim[3])
+        rows = a4[c3.clamp(0, a_dim[3] - 1), c2.clamp(0, a_dim[2] - 1), c1.clamp(0, a_dim[1] - 1)].double()
+        rows = rows * ok[:, None]
+        acc += rows[:, :K] @ b3[j].double()[:, :K].t()
+    return acc

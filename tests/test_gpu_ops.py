@@ -1,0 +1,256 @@
+"""Kernel-level parity on the GPU: every C ABI entry point against an fp64 torch restatement of its definition."""
+import math
+
+import pytest
+import torch
+
+from conftest import rel_l2
+from helpers import gemm_reference
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+def _ops():
+    from dist_b200 import ops
+    return ops
+
+
+def _run(call):
+    call.launch(torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+
+
+def _qgelu(x):
+    return x * torch.sigmoid(1.702 * x)
+
+
+# scenario: a_shape = logical A as a torch tensor [c3, c2, c1, k_pitch]
+SCENARIOS = {
+    "plain_ragged": dict(a_shape=(1, 1, 300, 104), k=100, n=80, taps=[(0, 0, 0)], groups=1, rpg=300),
+    "plain_vit": dict(a_shape=(1, 1, 1000, 768), k=768, n=256, taps=[(0, 0, 0)], groups=1, rpg=1000),
+    "plain_wide": dict(a_shape=(1, 1, 520, 256), k=256, n=2304, taps=[(0, 0, 0)], groups=1, rpg=520),
+    "n384": dict(a_shape=(1, 1, 394, 768), k=768, n=384, taps=[(0, 0, 0)], groups=1, rpg=394),
+    "k96_n96": dict(a_shape=(1, 1, 777, 96), k=96, n=96, taps=[(0, 0, 0)], groups=1, rpg=777),
+    "long_k": dict(a_shape=(1, 1, 256, 3072), k=3072, n=768, taps=[(0, 0, 0)], groups=1, rpg=256),
+    "small_m": dict(a_shape=(1, 1, 2, 384), k=384, n=1536, taps=[(0, 0, 0)], groups=1, rpg=2),
+    # (kt,1,1) conv over a clip: 3 taps, row shift +-P, zero padded inside each group
+    "conv_t": dict(a_shape=(1, 3, 4 * 49, 96), k=96, n=96, taps=[(-49, 0, 0), (0, 0, 0), (49, 0, 0)], groups=3, rpg=4 * 49),
+    # stem-like: 5 taps, padded K pitch
+    "stem": dict(a_shape=(1, 2, 6 * 16, 592), k=588, n=96, taps=[((k - 2) * 16, 0, 0) for k in range(5)], groups=2, rpg=6 * 16),
+    # (1,3,3) conv on a 14x14 grid: image mode, 9 taps
+    "conv_s14": dict(a_shape=(5, 14, 14, 96), k=96, n=96, img_w=14, taps=[(j - 1, i - 1, 0) for i in range(3) for j in range(3)], groups=5, rpg=196),
+    "conv_s16": dict(a_shape=(3, 16, 16, 96), k=96, n=96, img_w=16, taps=[(j - 1, i - 1, 0) for i in range(3) for j in range(3)], groups=3, rpg=256),
+    # temporal -> integration: taps along dim 2, group on dim 3, rows written behind a class row
+    "t2i": dict(a_shape=(6, 2, 196, 96), k=96, n=384, taps=[(0, 0, 0), (0, 1, 0)], groups=6, rpg=196, group_dim=3,
+                out_gstride=197, out_roff=1, out_rows=6 * 197),
+    # integration -> temporal: skip the class row on the input, replicate rows on the output
+    "i2t": dict(a_shape=(1, 6, 197, 384), k=384, n=96, taps=[(1, 0, 0)], groups=6, rpg=196, out_gstride=2 * 196, out_rep=2,
+                out_rep_stride=196, out_rows=12 * 196),
+}
+
+
+def _build(sc, dtype, seed=0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    a = torch.randn(*sc["a_shape"], generator=g)
+    k, n, taps = sc["k"], sc["n"], sc["taps"]
+    kp = sc["a_shape"][-1]
+    a[..., k:] = 7.0        # pad columns must never be read
+    b = torch.randn(len(taps), n, kp, generator=g) / math.sqrt(k * len(taps))
+    b[..., k:] = 7.0
+    bias = torch.randn(n, generator=g)
+    out_rows = sc.get("out_rows", sc["groups"] * sc["rpg"])
+    res = torch.randn(out_rows, n, generator=g)
+    return a.to(DEV, dtype), b.to(DEV, dtype), bias.to(DEV), res.to(DEV)
+
+
+def _expected(sc, a, b, bias, res, use_bias, use_res, act):
+    shp = sc["a_shape"]
+    a_dim = (sc["k"], shp[2], shp[1], shp[0])
+    acc = gemm_reference(a.double(), a_dim, sc["taps"], b.double(), sc["groups"], sc["rpg"], sc.get("img_w", 0), sc.get("group_dim", 2))
+    out_rows = sc.get("out_rows", sc["groups"] * sc["rpg"])
+    gs, ro = sc.get("out_gstride", sc["rpg"]), sc.get("out_roff", 0)
+    rep, rs = sc.get("out_rep", 1), sc.get("out_rep_stride", 0)
+    exp = torch.full((out_rows, sc["n"]), float("nan"), dtype=torch.float64, device=a.device)
+    gi = torch.arange(sc["groups"], device=a.device).repeat_interleave(sc["rpg"])
+    r = torch.arange(sc["rpg"], device=a.device).repeat(sc["groups"])
+    for q in range(rep):
+        rows = gi * gs + ro + r + q * rs
+        v = acc.clone()
+        if use_bias:
+            v = v + bias.double()
+        if use_res:
+            v = v + res.double()[rows]
+        if act:
+            v = _qgelu(v)
+        exp[rows] = v
+    return exp
+
+
+def _call(ops, sc, a, b, bias, res, out, out2, use_bias, use_res, act, impl):
+    shp = sc["a_shape"]
+    kp = shp[-1]
+    a_dim = (sc["k"], shp[2], shp[1], shp[0])
+    a_stride = (1, kp, kp * shp[2], kp * shp[2] * shp[1])
+    n = sc["n"]
+    return ops.gemm(a, b, n, sc["k"], a_dim=a_dim, a_stride=a_stride, taps=sc["taps"], b_tap_stride=n * kp, ldb=kp,
+                    img_w=sc.get("img_w", 0), groups=sc["groups"], rows_per_group=sc["rpg"], group_dim=sc.get("group_dim", 2),
+                    bias=bias if use_bias else None, res=res if use_res else None, ld_res=n,
+                    res_gstride=sc.get("out_gstride", sc["rpg"]), res_roff=sc.get("out_roff", 0), res_rep_stride=sc.get("out_rep_stride", 0),
+                    out=out, ld_out=n, out_gstride=sc.get("out_gstride", sc["rpg"]), out_roff=sc.get("out_roff", 0),
+                    out_rep=sc.get("out_rep", 1), out_rep_stride=sc.get("out_rep_stride", 0), out2=out2, ld_out2=n,
+                    act=ops.ACT_QUICKGELU if act else ops.ACT_NONE, impl=impl)
+
+
+@pytest.mark.parametrize("name", list(SCENARIOS))
+@pytest.mark.parametrize("mode", ["simt_fp32", "simt_bf16", "tcgen05"])
+def test_gemm(name, mode):
+    ops = _ops()
+    sc = SCENARIOS[name]
+    dtype = torch.float32 if mode == "simt_fp32" else torch.bfloat16
+    impl = ops.IMPL_TCGEN05 if mode == "tcgen05" else ops.IMPL_SIMT
+    if mode == "tcgen05" and sc["n"] % 16:
+        pytest.skip("tcgen05 path needs n % 16 == 0")
+    a, b, bias, res = _build(sc, dtype)
+    out_rows = sc.get("out_rows", sc["groups"] * sc["rpg"])
+    for use_bias, use_res, act in [(False, False, False), (True, True, True), (True, False, True), (True, True, False)]:
+        out = torch.full((out_rows, sc["n"]), float("nan"), device=DEV, dtype=torch.float32)
+        out2 = torch.full((out_rows, sc["n"]), float("nan"), device=DEV, dtype=dtype)
+        _run(_call(ops, sc, a, b, bias, res, out, out2, use_bias, use_res, act, impl))
+        exp = _expected(sc, a, b, bias, res, use_bias, use_res, act)
+        written = ~torch.isnan(exp)
+        assert torch.equal(torch.isnan(out), ~written), "rows outside the mapping were touched (or rows were skipped)"
+        tol = 2e-6 if mode == "simt_fp32" else 1e-5     # same (rounded) operands, fp32 accumulation
+        assert rel_l2(out[written], exp[written]) < tol, (name, mode, use_bias, use_res, act)
+        assert rel_l2(out2.float()[written], exp[written]) < (tol if dtype == torch.float32 else 3e-3)
+
+
+def test_gemm_in_place_residual_bf16_out():
+    ops = _ops()
+    g = torch.Generator().manual_seed(1)
+    a = torch.randn(640, 768, generator=g).to(DEV, torch.bfloat16)
+    w = (torch.randn(768, 768, generator=g) / 28).to(DEV, torch.bfloat16)
+    bias = torch.randn(768, generator=g).to(DEV)
+    h = torch.randn(640, 768, generator=g).to(DEV)
+    exp = h.double() + a.double() @ w.double().t() + bias.double()
+    tap = torch.empty(640, 768, device=DEV, dtype=torch.bfloat16)
+    _run(ops.gemm(a, w, 768, 768, bias=bias, res=h, ld_res=768, out=h, ld_out=768, out2=tap, ld_out2=768))
+    assert rel_l2(h, exp) < 1e-5
+    assert rel_l2(tap.float(), exp) < 3e-3
+
+
+def test_gemm_rejects_bad_arguments():
+    ops = _ops()
+    a = torch.zeros(8, 24, device=DEV, dtype=torch.bfloat16)
+    w = torch.zeros(24, 24, device=DEV, dtype=torch.bfloat16)
+    out = torch.zeros(8, 24, device=DEV)
+    with pytest.raises(ops.DistB200Error):          # n % 16 != 0 on the tensor-core path
+        _run(ops.gemm(a, w, 24, 24, out=out, ld_out=24))
+    with pytest.raises(ops.DistB200Error):          # no output
+        _run(ops.gemm(a, w, 24, 24))
+
+
+@pytest.mark.parametrize("cols,rows", [(768, 1000), (1024, 77), (384, 515), (96, 3000), (128, 5), (32, 64)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_layernorm(cols, rows, dtype):
+    ops = _ops()
+    g = torch.Generator().manual_seed(cols)
+    x = (torch.randn(rows, cols, generator=g) * 3 + 1).to(DEV)
+    add = torch.randn(7, cols, generator=g).to(DEV)
+    g1, b1, g2, b2 = [torch.randn(cols, generator=g).to(DEV) for _ in range(4)]
+    y1 = torch.empty(rows, cols, device=DEV, dtype=dtype)
+    y2 = torch.empty(rows, cols, device=DEV, dtype=dtype)
+    _run(ops.layernorm(x, g1, b1, y1, in2=add, in2_period=7, g2=g2, b2=b2, y2=y2))
+    xx = x.double() + add.double()[torch.arange(rows, device=DEV) % 7]
+    n = (xx - xx.mean(-1, keepdim=True)) / torch.sqrt(xx.var(-1, unbiased=False, keepdim=True) + 1e-5)
+    tol = 2e-6 if dtype == torch.float32 else 3e-3
+    assert rel_l2(y1.float(), n * g1.double() + b1.double()) < tol
+    assert rel_l2(y2.float(), n * g2.double() + b2.double()) < tol
+    if dtype == torch.float32:      # in place
+        _run(ops.layernorm(x, g1, b1, x))
+        n = (xx - add.double()[torch.arange(rows, device=DEV) % 7])
+        n = (n - n.mean(-1, keepdim=True)) / torch.sqrt(n.var(-1, unbiased=False, keepdim=True) + 1e-5)
+        assert rel_l2(x, n * g1.double() + b1.double()) < 2e-6
+
+
+def _attention_ref(qkv, frames, tokens, heads):
+    D = heads * 64
+    q, k, v = qkv.double().view(frames, tokens, 3, heads, 64).permute(2, 0, 3, 1, 4)
+    att = torch.softmax(q @ k.transpose(-1, -2) / 8.0, dim=-1)
+    return (att @ v).permute(0, 2, 1, 3).reshape(frames, tokens, D)
+
+
+@pytest.mark.parametrize("tokens,heads,frames", [(197, 12, 3), (257, 16, 2), (17, 2, 5), (50, 1, 1)])
+@pytest.mark.parametrize("mode", ["simt_fp32", "simt_bf16", "tc_bf16"])
+def test_attention(tokens, heads, frames, mode):
+    ops = _ops()
+    dtype = torch.float32 if mode == "simt_fp32" else torch.bfloat16
+    g = torch.Generator().manual_seed(tokens)
+    qkv = (torch.randn(frames, tokens, 3 * heads * 64, generator=g) * 1.5).to(DEV, dtype)
+    out = torch.full((frames, tokens, heads * 64), float("nan"), device=DEV, dtype=dtype)
+    impl = ops.IMPL_SIMT if mode.startswith("simt") else ops.IMPL_AUTO
+    _run(ops.attention(qkv, out, frames, tokens, heads, impl=impl))
+    exp = _attention_ref(qkv, frames, tokens, heads)
+    assert rel_l2(out.float(), exp) < (3e-6 if dtype == torch.float32 else 6e-3)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("keys,batch", [(197, 9), (8, 3), (257, 2)])
+def test_cross_attention(dtype, keys, batch):
+    ops = _ops()
+    heads, C = 6, 384
+    g = torch.Generator().manual_seed(keys)
+    q = torch.randn(batch, C, generator=g).to(DEV, dtype)
+    kv = torch.randn(batch, keys, 2 * C, generator=g).to(DEV, dtype)
+    out = torch.empty(batch, C, device=DEV, dtype=dtype)
+    _run(ops.cross_attention(q, kv, out, batch, keys, heads))
+    qh = q.double().view(batch, heads, 1, 64)
+    k = kv.double()[..., :C].view(batch, keys, heads, 64).transpose(1, 2)
+    v = kv.double()[..., C:].view(batch, keys, heads, 64).transpose(1, 2)
+    exp = (torch.softmax(qh @ k.transpose(-1, -2) / 8.0, -1) @ v).reshape(batch, C)
+    assert rel_l2(out.float(), exp) < (3e-6 if dtype == torch.float32 else 6e-3)
+
+
+@pytest.mark.parametrize("p,res,pitch", [(16, 64, 768), (14, 56, 592), (16, 224, 768)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_patchify(p, res, pitch, dtype):
+    ops = _ops()
+    from oracle import dist_oracle
+    clips, T, step = 2, 6, 2
+    g = torch.Generator().manual_seed(p)
+    video = torch.randn(clips, 3, T, res, res, generator=g).to(DEV)
+    n_sel = T // step
+    P = (res // p) ** 2
+    out = torch.full((clips * n_sel * P, pitch), float("nan"), device=DEV, dtype=dtype)
+    _run(ops.patchify(video, out, clips, T, res, res, p, 0, step, n_sel, pitch))
+    frames = video[:, :, ::step].permute(0, 2, 1, 3, 4).reshape(-1, 3, res, res)
+    exp = dist_oracle.patchify(frames.cpu(), p).reshape(-1, 3 * p * p)
+    assert torch.equal(out[:, :3 * p * p].float().cpu(), exp.to(dtype).float())     # a pure permutation (+ cast)
+    assert (out[:, 3 * p * p:] == 0).all()
+
+
+def test_small_kernels():
+    ops = _ops()
+    g = torch.Generator().manual_seed(3)
+    dst = torch.randn(10, 5, 16, generator=g).to(DEV)
+    table = torch.randn(4, 16, generator=g).to(DEV)
+    before = dst.clone()
+    _run(ops.rows_bcast(dst, 5 * 16, 10, 16, table, 4, True))
+    exp = before.clone()
+    exp[:, 0] += table[torch.arange(10) % 4]
+    assert torch.allclose(dst, exp)
+    _run(ops.rows_bcast(dst, 5 * 16, 10, 16, table, 1, False))
+    exp[:, 0] = table[0]
+    assert torch.allclose(dst, exp)
+    src = torch.randn(3 * 4, 7, 32, generator=g).to(DEV)        # [(b, i), token, col]
+    out = torch.empty(3, 32, device=DEV)
+    _run(ops.mean_rows(src, 7 * 32, 4, 3, 32, out))
+    assert torch.allclose(out, src[:, 0].view(3, 4, 32).mean(1), atol=1e-6)
+    emb = torch.randn(5, 64, generator=g).to(DEV)
+    text = torch.randn(11, 64, generator=g).to(DEV)
+    text_n = text / text.norm(dim=1, keepdim=True)
+    logits, probs = torch.empty(5, 11, device=DEV), torch.empty(5, 11, device=DEV)
+    _run(ops.class_head(emb, text_n, 14.2857, 5, 64, 11, logits, probs))
+    exp = 14.2857 * (emb.double() / emb.double().norm(dim=1, keepdim=True)) @ text_n.double().t()
+    assert rel_l2(logits, exp) < 2e-6 and rel_l2(probs, torch.softmax(exp, -1)) < 2e-6

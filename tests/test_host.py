@@ -1,0 +1,157 @@
+"""Host-side logic: config schema, registries, builders, weights contract, C ABI surface (no GPU needed)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from conftest import ROOT
+from dist_b200 import build as dbuild
+from dist_b200.arch import arch_from_cfg, tiny_arch, DistArch
+from dist_b200.config import Config
+from dist_b200.registry import Registry
+from dist_b200.utils import synth
+
+CFG_DIR = os.path.join(ROOT, "configs", "projects", "dist")
+
+
+def test_registry_semantics():
+    reg = Registry("T")
+
+    @reg.register()
+    class Foo:
+        pass
+
+    assert reg.get("Foo") is Foo and reg.get("Bar") is None and "Foo" in reg.get_all_registered()
+    with pytest.raises(AssertionError):
+        reg.register()(Foo)
+
+
+@pytest.mark.parametrize("path,frames,ada,classes,name", [
+    ("ssv2/vit-b16-8+16f.yaml", 16, 2, 174, "ViT-B-16"),
+    ("ssv2/vit-b16-16+32f.yaml", 32, 2, 174, "ViT-B-16"),
+    ("k400/vit-b16-32+64f.yaml", 64, 4, 400, "ViT-B-16"),
+    ("k400/vit-l14-32+64f.yaml", 64, 4, 400, "ViT-L-14"),
+    ("ssv2/vit-l14-32+64f.yaml", 64, 2, 174, "ViT-L-14"),
+])
+def test_config_inheritance(path, frames, ada, classes, name):
+    cfg = Config.from_file(os.path.join(CFG_DIR, path))
+    assert cfg.DATA.NUM_INPUT_FRAMES == frames and cfg.DATA.SPARSE_SAMPLE_ALPHA == 2
+    assert cfg.VIDEO.BACKBONE.DIST.ADA_POOLING_LAYERS == ada
+    assert cfg.VIDEO.HEAD.NUM_CLASSES == classes and cfg.VIDEO.HEAD.NAME == "ClipVideoTextIdentity"
+    assert cfg.VIDEO.BACKBONE.META_ARCH == "ClipVisionTextTransformer" and cfg.VIDEO.BACKBONE.META_ARCH_NAME == name
+    assert cfg.VIDEO.BACKBONE.ATTEN_BLOCK == "ResidualAttentionBlockMid"
+    assert cfg.OPTIMIZER.BASE_LR == pytest.approx(3.2e-5) and isinstance(cfg.OPTIMIZER.MIN_LR, float)
+    assert cfg.DIST_BACKEND == "nccl"                       # from pool/base.yaml
+    assert cfg.OPTIMIZER.OPTIM_METHOD == "adamw"            # _BASE_RUN overridden by the project base
+    arch = arch_from_cfg(cfg)
+    assert arch.tokens == (197 if name == "ViT-B-16" else 257)
+
+
+def test_config_overrides():
+    cfg = Config.from_file(os.path.join(CFG_DIR, "ssv2/vit-b16-8+16f.yaml"),
+                           ["DATA.NUM_INPUT_FRAMES", "32", "VIDEO.BACKBONE.DIST.ADA_POOLING_LAYERS", "3", "NUM_GPUS", "0"])
+    assert cfg.DATA.NUM_INPUT_FRAMES == 32 and cfg.VIDEO.BACKBONE.DIST.ADA_POOLING_LAYERS == 3 and cfg.NUM_GPUS == 0
+    with pytest.raises(AssertionError):
+        Config.from_file(os.path.join(CFG_DIR, "ssv2/vit-b16-8+16f.yaml"), ["DATA.NO_SUCH_KEY", "1"])
+    with pytest.raises(AssertionError):
+        Config.from_file(os.path.join(CFG_DIR, "ssv2/vit-b16-8+16f.yaml"), ["DATA.NUM_INPUT_FRAMES"])
+
+
+def test_l14_patch_mismatch_is_rejected():
+    with pytest.raises(AssertionError):
+        DistArch(width=1024, layers=24, patch=14, embed_dim=768, s_patch=16, selected_layers=list(range(24))).validate()
+
+
+def test_registry_driven_build_and_weights_contract():
+    import dist_b200.models.base  # noqa: F401  (registration side effects)
+    from dist_b200.models.base.backbone import BACKBONE_REGISTRY
+    from dist_b200.models.base.base_blocks import BRANCH_REGISTRY, HEAD_REGISTRY, STEM_REGISTRY
+    from dist_b200.models.base.builder import build_model
+    from dist_b200.models.base.clip import ATTEN_BLOCK_REGISTRY
+    from dist_b200.models.base.models import MODEL_REGISTRY, BaseVideoModel
+
+    assert BACKBONE_REGISTRY.get("ClipVisionTextTransformer") is not None
+    assert ATTEN_BLOCK_REGISTRY.get("ResidualAttentionBlockMid") is not None
+    assert HEAD_REGISTRY.get("ClipVideoTextIdentity") is not None
+    for name in ("DiSTNetwork", "TemporalNet", "IntegrationNetwork", "Integration2TemporalNetwork",
+                 "Temporal2IntegrationNetwork", "SpatialTemporalAdaPoolingNetwork"):
+        assert BRANCH_REGISTRY.get(name) is not None
+    assert STEM_REGISTRY.get("DiSTTemporalStem") is not None
+    assert MODEL_REGISTRY.get("clip") is None              # falls back to BaseVideoModel (builder.py:30-32)
+
+    cfg = Config.from_file(os.path.join(CFG_DIR, "ssv2/vit-b16-8+16f.yaml"), ["NUM_GPUS", "0"])
+    model, ema = build_model(cfg)
+    assert isinstance(model, BaseVideoModel) and ema is None
+    enc = model.backbone.base_encoder
+    assert model.backbone.get_num_layers() == (12, 0)
+    sd = synth.synth_state_dict(arch_from_cfg(cfg), seed=0)
+    own = enc.state_dict()
+    assert set(own) == set(sd)                              # the reference's key names (checked against it in make_golden.py)
+    assert all(own[k].shape == sd[k].shape for k in sd)
+    n_dist = sum(v.numel() for k, v in own.items() if k.startswith("dist_net."))
+    assert n_dist == 19001184                               # 19.00 M
+    # no CPU fallback: running without a GPU must fail loudly, not silently compute something else
+    with pytest.raises(RuntimeError):
+        model({"video": torch.zeros(1, 3, 16, 224, 224), "texts": torch.zeros(174, 512)})
+
+
+def test_head_semantics():
+    from dist_b200.models.base.base_blocks import ClipVideoTextIdentity
+    cfg = Config.from_file(os.path.join(CFG_DIR, "ssv2/vit-b16-8+16f.yaml"))
+    head = ClipVideoTextIdentity(cfg).eval()
+    x = {"logits_per_image": torch.randn(3, 2, 7)}
+    out, passthrough = head(x)
+    assert torch.allclose(out, torch.softmax(x["logits_per_image"].mean(1), -1)) and passthrough is x
+    head.train()
+    out, _ = head(x)
+    assert torch.allclose(out, x["logits_per_image"].mean(1))
+
+
+def test_synth_is_deterministic():
+    a = tiny_arch()
+    s1, s2 = synth.synth_state_dict(a, 0, "scaled"), synth.synth_state_dict(a, 0, "scaled")
+    assert all(torch.equal(s1[k], s2[k]) for k in s1)
+    assert not torch.equal(synth.synth_state_dict(a, 1, "scaled")["dist_net.proj"], s1["dist_net.proj"])
+    assert torch.equal(synth.synth_clips(2, a, 5), synth.synth_clips(2, a, 5))
+
+
+def test_flop_model_matches_survey():
+    # torch FlopCounterMode on the reference gives 314.3 GF/clip (B/16 8+16f): that count includes 1.85 GF of
+    # discarded patch-embed work and omits the attention matmuls (SDPA is not counted on CPU); SURVEY.md 8(d)'s
+    # formula, implemented by flops_per_clip, counts attention and only the useful patch embedding.
+    a = DistArch()
+    f = a.flops_per_clip()
+    attn = a.layers * a.sparse_frames * 4 * a.tokens ** 2 * a.width
+    assert abs((f["total"] - attn) / 1e9 - (314.3 - 1.85)) < 2.0
+    big = DistArch(width=1024, layers=24, patch=14, embed_dim=768, frames=64, s_patch=14, ada_layers=4,
+                   selected_layers=list(range(24)))
+    fb = big.flops_per_clip()
+    attn = big.layers * big.sparse_frames * 4 * big.tokens ** 2 * big.width
+    wasted = 2 * big.sparse_frames * big.patches * big.width * 3 * big.patch ** 2
+    assert abs((fb["total"] - attn + wasted) / 1e9 - 5458.1) / 5458.1 < 0.01
+
+
+def test_c_abi_exports_every_declared_symbol():
+    """The shared library loads and exports what include/distb200.h declares (no compute without a GPU)."""
+    header = open(os.path.join(ROOT, "include", "distb200.h")).read()
+    declared = sorted(set(re.findall(r"\b(distb200_[a-z_0-9]+)\s*\(", header)))
+    assert "distb200_gemm" in declared and len(declared) >= 11
+    lib_path = dbuild.build()
+    lib = ctypes.CDLL(lib_path)
+    for sym in declared:
+        assert hasattr(lib, sym), sym
+    lib.distb200_version.restype = ctypes.c_int
+    assert lib.distb200_version() == 100
+    from dist_b200 import ops
+    assert sorted(ops.EXPORTS) == declared
+    # the ctypes mirror of the descriptor must have the C layout
+    import subprocess, tempfile
+    src = '#include <stdio.h>\n#include <stddef.h>\n#include "distb200.h"\nint main(){printf("%zu %zu %zu %zu", sizeof(distb200_gemm_desc), offsetof(distb200_gemm_desc, ldb), offsetof(distb200_gemm_desc, out), offsetof(distb200_gemm_desc, group_dim));return 0;}'
+    with tempfile.TemporaryDirectory() as td:
+        open(os.path.join(td, "t.c"), "w").write(src)
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), os.path.join(td, "t.c"), "-o", os.path.join(td, "t")])
+        sizes = [int(x) for x in subprocess.check_output([os.path.join(td, "t")]).split()]
+    D = ops.GemmDesc
+    assert sizes == [ctypes.sizeof(D), D.ldb.offset, D.out.offset, D.group_dim.offset]
