@@ -1,0 +1,347 @@
+#!/usr/bin/env python3
+"""Benchmark of the DiST video forward path (BASELINE.json: clips/sec, ViT-B/16 8+16f, 32 clips per GPU, bf16).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload b16_8x16|b16_32x64|l14_32x64]
+
+One step = one forward of ``--clips`` (default 32) synthetic clips per GPU through the planned CUDA path
+(CUDA-graph replay).  Rank 0 prints ONE JSON line:
+
+  value      clips/s over all GPUs with the clips already resident in HBM, timed with CUDA events, max over ranks
+  e2e        the same metric through the public API (``build_model(cfg)`` -> ``model({"video","texts"})``) with the
+             clips in pinned HOST memory: H2D copy of the step's clips and D2H read of its class probabilities are
+             inside the timed region
+  roofline   the dominant kernel (tcgen05 GEMM): algorithmic FLOPs of its launches / their summed CUDA-event time
+             (measured in a separate instrumented pass of the same plan), against MEASURED_PEAKS.json
+  cpu_baseline  the oracle port (oracle/dist_oracle.py, fp32, all host threads) on a bounded sample of the workload
+  kernels    time share per kernel family from the instrumented pass
+
+``--impl reference`` times the CPU path only (rank 0; other ranks exit): the reference is PyTorch code that cannot
+travel to the GPU box, so the arm runs the oracle port - the same torch-CPU tensor algebra - on the host cores.
+Multi-GPU: one process per GPU (torchrun), clips sharded by rank, weights replicated, the only collective is the
+all-gather of the per-clip class probabilities each step (runs/test.py:133 in the reference).
+"""
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+from dist_b200.arch import DistArch  # noqa: E402
+from dist_b200.utils import synth  # noqa: E402
+
+WORKLOADS = {
+    "b16_8x16": dict(arch=dict(), cfg="configs/projects/dist/ssv2/vit-b16-8+16f.yaml", label="DiST ViT-B/16 8+16f SSV2"),
+    "b16_32x64": dict(arch=dict(frames=64, ada_layers=4, num_classes=400), cfg="configs/projects/dist/k400/vit-b16-32+64f.yaml",
+                      label="DiST ViT-B/16 32+64f K400"),
+    "l14_32x64": dict(arch=dict(width=1024, layers=24, patch=14, embed_dim=768, frames=64, s_patch=14, ada_layers=4,
+                                num_classes=400, selected_layers=list(range(24))),
+                      cfg="configs/projects/dist/k400/vit-l14-32+64f.yaml", label="DiST ViT-L/14 32+64f K400"),
+}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sustained=d["bf16_tflops_sustained"], source="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for r in self.rows if len(r) >= 7]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm = [float(r[0]) for r in rows]
+        busy = [s for s in sm if s > 0.5 * max(sm)] or sm
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in rows)]
+        return {"sm_mhz": statistics.median(busy), "sm_max_mhz": float(rows[0][1]), "power_w_max": max(float(r[2]) for r in rows),
+                "reasons": reasons, "samples": len(rows)}
+
+
+def cpu_reference(arch, sd, sample_clips, repeats):
+    """Oracle port, fp32, all host threads; returns (clips/s, cores, description)."""
+    from oracle import dist_oracle
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    clips = synth.synth_clips(sample_clips, arch, seed=1234, kind="structured")
+    with torch.no_grad():
+        dist_oracle.forward_arch(sd, clips[:1], arch, dtype=torch.float32)          # warm-up
+        times = []
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            dist_oracle.forward_arch(sd, clips, arch, dtype=torch.float32)
+            times.append(time.perf_counter() - t0)
+    best = statistics.median(times)
+    return sample_clips / best, cores, "%d x forward of %d clip(s), fp32, median" % (repeats, sample_clips)
+
+
+def run_reference_arm(args, arch, label):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sd = synth.synth_state_dict(arch, seed=0, init="reference")
+    sample = 2 if arch.width < 1024 and arch.frames <= 16 else 1
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    from oracle import dist_oracle
+    clips = synth.synth_clips(sample, arch, seed=1234, kind="structured")
+    steps = max(1, min(args.steps, 5))
+    warm = max(1, min(args.warmup, 1))
+    with torch.no_grad():
+        for _ in range(warm):
+            dist_oracle.forward_arch(sd, clips, arch, dtype=torch.float32)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            dist_oracle.forward_arch(sd, clips, arch, dtype=torch.float32)
+        el = time.perf_counter() - t0
+    value = sample * steps / el
+    line = {
+        "impl": "reference", "metric": "clips/sec", "value": value, "unit": "clips/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm,
+        "ms_per_step": el / steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": label + " forward, CPU oracle port of the reference path", "clips_per_step": sample},
+        "cpu_baseline": {"value": value, "unit": "clips/s", "cores": cores, "kind": "port",
+                         "sample": "%d steps x %d clip(s) per step, fp32, %d threads" % (steps, sample, cores)},
+        "e2e": {"value": value, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def instrumented_pass(eng, reps=3):
+    """Replay the plan eagerly with a CUDA event pair around every call; returns per-family stats."""
+    stream = torch.cuda.current_stream()
+    fam = {}
+    for rep in range(reps + 1):
+        evs = []
+        for c in eng.calls:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            c.launch(stream.cuda_stream)
+            e1.record(stream)
+            evs.append((c, e0, e1))
+        torch.cuda.synchronize()
+        if rep == 0:
+            continue        # warm-up
+        for c, e0, e1 in evs:
+            key = family(c)
+            f = fam.setdefault(key, dict(ms=0.0, flops=0, bytes=0, launches=0))
+            f["ms"] += e0.elapsed_time(e1)
+            f["flops"] += c.flops
+            f["bytes"] += c.bytes
+            f["launches"] += 1
+    for f in fam.values():
+        f["ms"] /= reps
+        f["flops"] //= reps
+        f["bytes"] //= reps
+        f["launches"] //= reps
+    return fam
+
+
+def family(call):
+    n = call.name
+    if n.startswith("patchify"):
+        return "patchify"
+    if "attention" in n or n.endswith(".attn"):
+        return "attention" if n.startswith("vit") else "cross_attention"
+    if n.endswith((".ln", ".ln_1", ".ln_2", ".ln_pre", ".ln_kv", ".ln_q", ".ln_out", "ln_post")) or ".ln" in n:
+        return "layernorm"
+    if "cls" in n and ("rows" in n or n.endswith(".cls")) or n.startswith("ada.init"):
+        return "rows_bcast"
+    if n.endswith("cls_mean"):
+        return "mean_rows"
+    if n.startswith("head."):
+        return "class_head"
+    return "gemm_vit" if n.startswith("vit.") else "gemm_dist"
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="dist_b200", choices=["dist_b200", "reference"])
+    ap.add_argument("--workload", default="b16_8x16", choices=list(WORKLOADS))
+    ap.add_argument("--clips", type=int, default=32, help="clips per GPU per step")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
+
+    wl = WORKLOADS[args.workload]
+    arch = DistArch(**wl["arch"]).validate()
+    if args.impl == "reference":
+        run_reference_arm(args, arch, wl["label"])
+        return
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    import torch.distributed as dist
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    from dist_b200.engine import DistEngine
+    sd = synth.synth_state_dict(arch, seed=0, init="reference")
+    text = synth.synth_text_features(arch.num_classes, arch.embed_dim)
+    b = args.clips
+    # clips: a few distinct structured clips tiled to the batch (generation cost only), different per rank
+    base = synth.synth_clips(min(b, 4), arch, seed=1234 + rank, kind="structured")
+    clips = base.repeat((b + base.shape[0] - 1) // base.shape[0], 1, 1, 1, 1)[:b].contiguous()
+
+    eng = DistEngine(sd, arch, b, device=dev, precision=args.precision, text_features=text)
+    eng.video.copy_(clips)
+    eng.capture()
+    gathered = torch.empty(world * b, eng.probs.shape[1], device=dev) if world > 1 else None
+
+    def step():
+        eng.graph.replay()
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, eng.probs)      # the logits gather of runs/test.py:133
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = float(ms.item())
+    value = world * b * args.steps / (total_ms / 1e3)
+
+    # ---- end to end through the public API, host buffers ----
+    e2e = None
+    if not args.no_e2e:
+        import dist_b200.models.base  # noqa: F401
+        from dist_b200.config import Config
+        from dist_b200.models.base.builder import build_model
+        cfg = Config.from_file(os.path.join(ROOT, wl["cfg"]), ["NUM_GPUS", "1", "B200.PRECISION", args.precision])
+        model, _ = build_model(cfg, gpu_id=local)
+        model.eval()
+        enc = model.module.backbone.base_encoder if hasattr(model, "module") else model.backbone.base_encoder
+        enc.load_state_dict(sd, strict=True)
+        host = [clips.clone().pin_memory(), clips.flip(0).clone().pin_memory()]
+        text_dev = text.to(dev)
+        out_host = torch.empty(b, text.shape[0]).pin_memory()
+
+        def e2e_step(i):
+            preds, _ = model({"video": host[i & 1], "texts": text_dev})     # H2D of the clips happens inside
+            out_host.copy_(preds, non_blocking=False)                        # D2H read of the result (syncs)
+            if world > 1:
+                dist.all_gather_into_tensor(gathered, preds.contiguous())
+
+        for i in range(args.warmup):
+            e2e_step(i)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        e0.record()
+        for i in range(args.steps):
+            e2e_step(i)
+        e1.record()
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        if world > 1:
+            dist.barrier()
+        ems = torch.tensor([max(e0.elapsed_time(e1), wall * 1e3)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ems, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * b * args.steps / (float(ems.item()) / 1e3), "unit": "clips/s",
+               "h2d_bytes_per_step": int(clips.numel() * 4), "d2h_bytes_per_step": int(out_host.numel() * 4),
+               "ms_per_step": float(ems.item()) / args.steps}
+        eng2 = next(iter(enc._engines.values()))[0]
+    else:
+        eng2 = eng
+
+    if rank == 0:
+        pk = peaks()
+        fam = instrumented_pass(eng2 if e2e is not None else eng)
+        tot = sum(f["ms"] for f in fam.values())
+        gemm_ms = fam.get("gemm_vit", {}).get("ms", 0.0) + fam.get("gemm_dist", {}).get("ms", 0.0)
+        gemm_fl = fam.get("gemm_vit", {}).get("flops", 0) + fam.get("gemm_dist", {}).get("flops", 0)
+        achieved = gemm_fl / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
+        kernels = {k: {"ms": round(v["ms"], 4), "share": round(v["ms"] / tot, 4), "launches": v["launches"],
+                       "tflops": round(v["flops"] / (v["ms"] / 1e3) / 1e12, 1) if v["ms"] > 0 else 0.0,
+                       "gbs": round(v["bytes"] / (v["ms"] / 1e3) / 1e9, 1) if v["ms"] > 0 else 0.0} for k, v in sorted(fam.items())}
+        cpu = None
+        if not args.no_cpu_baseline:
+            heavy = arch.width >= 1024 or arch.frames > 16
+            v, cores, sample = cpu_reference(arch, sd, 1 if heavy else 2, 1 if heavy else 3)
+            cpu = {"value": v, "unit": "clips/s", "cores": cores, "kind": "port", "sample": sample}
+        fl = arch.flops_per_clip()
+        line = {
+            "metric": "clips/sec", "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+            "config": {"workload": "%s inference, %d synthetic 224x224 clips per GPU, clip-sharded" % (wl["label"], b),
+                       "clips_per_gpu": b, "precision": args.precision, "cuda_graph": True,
+                       "l2": "per-step working set (%.1f GB of activations) exceeds the 126 MB L2; no explicit flush" % (
+                           sum(t.numel() * t.element_size() for t in vars(eng).values() if torch.is_tensor(t)) / 1e9),
+                       "gflop_per_clip": round(fl["total"] / 1e9, 1), "weights": "random init (reference distributions), seed 0"},
+            "model_tflops": value / world * fl["total"] / 1e12,
+            "roofline": {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (all %d GEMM launches of a step)" % (
+                             fam.get("gemm_vit", {}).get("launches", 0) + fam.get("gemm_dist", {}).get("launches", 0)),
+                         "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["tf_sustained"],
+                         "traffic": None, "peak_source": pk["source"] + " sustained bf16 (kernel timed inside a long step)"},
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": eng.num_launches * args.steps, "launches_per_step": eng.num_launches,
+            "kernels": kernels, "clocks": clocks,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -169,20 +169,25 @@ class CLIP(nn.Module):
             image = image.view(bt // self.num_frames, self.num_frames, c, h, w).permute(0, 2, 1, 3, 4).contiguous()
         return image
 
+    def _device_for(self, image):
+        """Clips may live on the model's GPU or in pinned host memory (copied straight into the engine's buffer)."""
+        dev = self.logit_scale.device
+        if dev.type != "cuda":
+            raise RuntimeError("dist_b200 runs on a CUDA device only; there is no CPU path (move the model with .cuda())")
+        if not image.is_cuda and not image.is_pinned():
+            raise RuntimeError("clips must be CUDA tensors or pinned host tensors")
+        return dev
+
     def forward_without_text(self, image):
-        if not image.is_cuda:
-            raise RuntimeError("dist_b200 runs on a CUDA device only; there is no CPU path")
         clips = self._as_clips(image)
-        eng = self._engine(clips.shape[0], clips.device, None)
+        eng = self._engine(clips.shape[0], self._device_for(image), None)
         emb = eng.forward(clips.float(), use_graph=self.use_graph)
         return emb.clone()[:, None, :]                                       # clip.py:480
 
     def forward_with_text(self, image, text, others=None):
-        if not image.is_cuda:
-            raise RuntimeError("dist_b200 runs on a CUDA device only; there is no CPU path")
         clips = self._as_clips(image)
         feats = self._text_from(text, others)
-        eng = self._engine(clips.shape[0], clips.device, feats)
+        eng = self._engine(clips.shape[0], self._device_for(image), feats)
         emb = eng.forward(clips.float(), use_graph=self.use_graph)
         logits = eng.logits.clone()
         vid = emb / emb.norm(dim=1, keepdim=True)                           # clip.py:513 (returned, not on the scored path)
