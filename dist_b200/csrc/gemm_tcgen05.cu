@@ -6,8 +6,11 @@
 //   warp 1        MMA issuer: one elected lane issues tcgen05.mma (M=128, N=block_n, K=16, bf16 x bf16 -> fp32)
 //                 into one of two TMEM accumulator stages; tcgen05.commit releases smem stages and publishes
 //                 the finished accumulator
-//   warps 2..5    epilogue: tcgen05.ld (one accumulator row per thread), bias + residual + QuickGELU, fp32 and/or
-//                 bf16 stores with the row remapping of include/distb200.h (so the next tile's MMAs overlap it)
+//   warps 2..9    epilogue (two warps per TMEM lane quadrant, alternating 32-column chunks): tcgen05.ld gives one
+//                 accumulator row per thread; the 32x32 block is transposed through a swizzled shared-memory
+//                 staging buffer so that lanes run along columns: bias, fp32 residual loads, QuickGELU and the
+//                 fp32 / bf16 stores are then fully coalesced (128 B per row), with the row remapping of
+//                 include/distb200.h.  The next tile's MMAs overlap the epilogue (two TMEM accumulator stages).
 //
 // Tile = rows_per_tile (<=128) output rows of one group x block_n columns; the reduction runs over
 // num_taps x ceil(K/64) k-blocks.  All rows of the 128-row MMA that lie outside the tile are computed on whatever
@@ -24,11 +27,13 @@ namespace {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;             // 64 bf16 = one 128-byte swizzle row
 constexpr int MAX_STAGES = 8;
-constexpr int NUM_THREADS = 192;
+constexpr int EPI_WARPS = 8;
+constexpr int NUM_THREADS = 64 + EPI_WARPS * 32;
+constexpr int STAGING_BYTES = EPI_WARPS * 32 * 32 * 4;
 constexpr uint32_t A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
 constexpr uint32_t TMEM_COLS = 512;
 constexpr uint32_t ACC_STAGE_COLS = 256;
-constexpr int SMEM_BUDGET = 200 * 1024;
+constexpr int SMEM_BUDGET = 227 * 1024 - STAGING_BYTES - 2048;
 
 struct alignas(64) TcArgs {
     CUtensorMap tm_a;
@@ -62,56 +67,154 @@ __device__ __forceinline__ TileCoord decode_tile(const TcArgs& a, long long tile
     return t;
 }
 
-__device__ __forceinline__ void store_chunk16(const distb200_gemm_desc& d, const uint32_t* acc, int n, long long dst_row,
-                                              long long res_row) {
-    float v[16];
+// sigmoid(1.702 x) = 0.5 + 0.5 tanh(0.851 x): one MUFU op for two values (tanh.approx.f16x2, |err| < 2^-10.9),
+// used for bf16 outputs where the rounding of the result dominates that error.
+__device__ __forceinline__ void quick_gelu_pair_fast(float& x0, float& x1) {
+    const __half2 h = __floats2half2_rn(0.851f * x0, 0.851f * x1);
+    uint32_t hi = *reinterpret_cast<const uint32_t*>(&h), ho;
+    asm("tanh.approx.f16x2 %0, %1;" : "=r"(ho) : "r"(hi));
+    const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&ho));
+    x0 = x0 * fmaf(0.5f, t.x, 0.5f);
+    x1 = x1 * fmaf(0.5f, t.y, 0.5f);
+}
+
+__device__ __forceinline__ float quick_gelu_precise(float x) { return __fdividef(x, 1.0f + __expf(-1.702f * x)); }
+
+// registers (thread = row) -> swizzled smem: 16-byte chunk j of row r lives at chunk slot (j ^ (r & 7))
+__device__ __forceinline__ void stage_block(const uint32_t* acc, float* stage, int lane) {
+    float4* st4 = reinterpret_cast<float4*>(stage);
 #pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(acc[i]);
-    if (d.bias) {
-        const float4* bp = reinterpret_cast<const float4*>(d.bias + n);
+    for (int j = 0; j < 8; ++j)
+        st4[lane * 8 + (j ^ (lane & 7))] = make_float4(__uint_as_float(acc[4 * j]), __uint_as_float(acc[4 * j + 1]),
+                                                       __uint_as_float(acc[4 * j + 2]), __uint_as_float(acc[4 * j + 3]));
+}
+
+// Epilogue variants (compile-time so that the inner loop carries no flag tests):
+//   OUT:  0 = fp32 `out`, 1 = bf16 `out`, 2 = fp32 `out` + bf16 `out2`, 3 = anything (runtime flags)
+//   ACT:  0 none, 1 QuickGELU via tanh.approx.f16x2, 2 QuickGELU via ex2 + rcp
+template <int OUT, bool RES, int ACT>
+struct Epi {
+    // Column domain: lanes 0-15 own the even rows, lanes 16-31 the odd rows of a 32 x 32 block; each lane owns two
+    // adjacent columns.  One loop iteration = two rows: 256 B of fp32 (or 128 B of bf16) per warp instruction.
+    static __device__ __forceinline__ void prefetch(const distb200_gemm_desc& d, float2* rv, long long res_row0, int n, int sub,
+                                                    int rows_here, bool col_ok) {
+        if (RES) {
+            const float* rp = d.res + (res_row0 + sub) * d.ld_res + n;
+            const long long step = 2 * d.ld_res;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const float4 b4 = __ldg(bp + i);
-            v[4 * i + 0] += b4.x; v[4 * i + 1] += b4.y; v[4 * i + 2] += b4.z; v[4 * i + 3] += b4.w;
+            for (int i = 0; i < 16; ++i) {
+                rv[i] = (col_ok && 2 * i + sub < rows_here) ? *reinterpret_cast<const float2*>(rp) : make_float2(0.f, 0.f);
+                rp += step;
+            }
         }
     }
-    if (d.res) {
-        const float4* rp = reinterpret_cast<const float4*>(d.res + res_row * d.ld_res + n);
+
+    static __device__ __forceinline__ void finish(const distb200_gemm_desc& d, const float* stage, const float2* rv, int lane, int n,
+                                                  int rows_here, long long dst_row0) {
+        const int sub = lane >> 4, cl = (lane & 15) * 2;
+        float2 bias = make_float2(0.f, 0.f);
+        if (d.bias) bias = __ldg(reinterpret_cast<const float2*>(d.bias + n));
+        const int chunk = cl >> 2, within = cl & 3;
+        char* o1 = nullptr;
+        char* o2 = nullptr;
+        long long s1 = 0, s2 = 0;
+        const bool f32_1 = OUT == 0 || OUT == 2 || (OUT == 3 && d.out_dtype == DISTB200_F32);
+        if (OUT != 3 || d.out) {
+            const int es = f32_1 ? 4 : 2;
+            o1 = reinterpret_cast<char*>(d.out) + ((dst_row0 + sub) * d.ld_out + n) * es;
+            s1 = 2 * d.ld_out * es;
+        }
+        const bool f32_2 = OUT == 3 && d.out2_dtype == DISTB200_F32;
+        if (OUT == 2 || (OUT == 3 && d.out2)) {
+            const int es = f32_2 ? 4 : 2;
+            o2 = reinterpret_cast<char*>(d.out2) + ((dst_row0 + sub) * d.ld_out2 + n) * es;
+            s2 = 2 * d.ld_out2 * es;
+        }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const float4 r4 = rp[i];
-            v[4 * i + 0] += r4.x; v[4 * i + 1] += r4.y; v[4 * i + 2] += r4.z; v[4 * i + 3] += r4.w;
+        for (int i = 0; i < 16; ++i) {
+            const int row = 2 * i + sub;
+            float2 v = *reinterpret_cast<const float2*>(stage + row * 32 + ((chunk ^ (row & 7)) << 2) + within);
+            v.x += bias.x;
+            v.y += bias.y;
+            if (RES) {
+                v.x += rv[i].x;
+                v.y += rv[i].y;
+            }
+            if (ACT == 1) quick_gelu_pair_fast(v.x, v.y);
+            if (ACT == 2) {
+                v.x = quick_gelu_precise(v.x);
+                v.y = quick_gelu_precise(v.y);
+            }
+            if (row < rows_here) {
+                if (o1) {
+                    if (f32_1) *reinterpret_cast<float2*>(o1) = v;
+                    else *reinterpret_cast<uint32_t*>(o1) = pack_bf16x2(v.x, v.y);
+                }
+                if (o2) {
+                    if (f32_2) *reinterpret_cast<float2*>(o2) = v;
+                    else *reinterpret_cast<uint32_t*>(o2) = pack_bf16x2(v.x, v.y);
+                }
+            }
+            o1 += s1;
+            o2 += s2;
         }
     }
-    if (d.act == DISTB200_ACT_QUICKGELU) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = quick_gelu(v[i]);
-    }
-    if (d.out) {
-        if (d.out_dtype == DISTB200_F32) {
-            float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(d.out) + dst_row * d.ld_out + n);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) op[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-        } else {
-            uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(d.out) + dst_row * d.ld_out + n);
-#pragma unroll
-            for (int i = 0; i < 2; ++i)
-                op[i] = make_uint4(pack_bf16x2(v[8 * i], v[8 * i + 1]), pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
-                                   pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
+};
+
+template <int OUT, bool RES, int ACT>
+__device__ __forceinline__ void epilogue_role(const TcArgs& args, uint32_t tmem_base, float* stage, uint32_t tfull0, uint32_t tempty0,
+                                              int warp, int lane) {
+    typedef Epi<OUT, RES, ACT> E;
+    const distb200_gemm_desc& d = args.d;
+    const int quad = warp & 3;              // TMEM lanes [32*quad, 32*quad+32) are the ones this warp may read
+    const int half = (warp - 2) >> 2;       // which of the alternating 32-column chunks
+    const int sub = lane >> 4, cl = (lane & 15) * 2;
+    int acc_stage = 0;
+    uint32_t acc_phase = 0;
+    for (long long tile = blockIdx.x; tile < args.total_tiles; tile += gridDim.x) {
+        const TileCoord tc = decode_tile(args, tile);
+        const long long rows_left = d.rows_per_group - tc.r0;
+        int rows_valid = (int)(rows_left < args.rows_per_tile ? rows_left : (long long)args.rows_per_tile) - quad * 32;
+        rows_valid = rows_valid > 32 ? 32 : rows_valid;                 // rows of this quadrant that exist
+        const long long r = (long long)tc.r0 + quad * 32;
+        const long long dst0 = tc.gi * d.out_gstride + d.out_roff + r;
+        const long long res0 = tc.gi * d.res_gstride + d.res_roff + r;
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)acc_stage * ACC_STAGE_COLS;
+        const int ncols = min(args.block_n, d.n - tc.n0);
+        bool waited = false;
+        for (int c0 = half * 32; c0 < ncols; c0 += 64) {
+            const int n = tc.n0 + c0 + cl;
+            const bool col_ok = c0 + cl < ncols;
+            float2 rv[16];
+            E::prefetch(d, rv, res0, n, sub, rows_valid, col_ok);      // in flight while the MMAs of the tile finish
+            if (!waited) {
+                ptx::mbar_wait(tfull0 + 8u * acc_stage, acc_phase);
+                ptx::tc_fence_after();
+                waited = true;
+            }
+            uint32_t acc[32];
+            const bool two = c0 + 16 < ncols;
+            ptx::tmem_ld16(taddr + (uint32_t)c0, acc);
+            if (two) ptx::tmem_ld16(taddr + (uint32_t)c0 + 16u, acc + 16);
+            ptx::tmem_ld_wait();
+            if (rows_valid > 0) {
+                stage_block(acc, stage, lane);
+                __syncwarp();
+                for (int rep = 0; rep < d.out_rep; ++rep) {
+                    if (rep > 0) E::prefetch(d, rv, res0 + (long long)rep * d.res_rep_stride, n, sub, rows_valid, col_ok);
+                    if (col_ok) E::finish(d, stage, rv, lane, n, rows_valid, dst0 + (long long)rep * d.out_rep_stride);
+                }
+                __syncwarp();
+            }
         }
-    }
-    if (d.out2) {
-        if (d.out2_dtype == DISTB200_F32) {
-            float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(d.out2) + dst_row * d.ld_out2 + n);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) op[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-        } else {
-            uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(d.out2) + dst_row * d.ld_out2 + n);
-#pragma unroll
-            for (int i = 0; i < 2; ++i)
-                op[i] = make_uint4(pack_bf16x2(v[8 * i], v[8 * i + 1]), pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
-                                   pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
+        if (!waited) {                       // this warp had no chunk in the tile: still observe the barrier phase
+            ptx::mbar_wait(tfull0 + 8u * acc_stage, acc_phase);
+            ptx::tc_fence_after();
         }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(tempty0 + 8u * acc_stage);
+        if (++acc_stage == 2) { acc_stage = 0; acc_phase ^= 1u; }
     }
 }
 
@@ -122,7 +225,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
     // carve shared memory: [stages x (A | B)] [barriers] ; swizzle-128B needs 1024-byte aligned stage bases
     const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t stage_bytes = A_STAGE_BYTES + args.b_stage_bytes;
-    const uint32_t bar_base = smem_base + (uint32_t)args.stages * stage_bytes;
+    const uint32_t staging_base = smem_base + (uint32_t)args.stages * stage_bytes;
+    const uint32_t bar_base = staging_base + STAGING_BYTES;
     // barriers (8 bytes each): full[MAX_STAGES], empty[MAX_STAGES], tmem_full[2], tmem_empty[2], then the TMEM base
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (MAX_STAGES + s); };
@@ -143,7 +247,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
         }
         for (int s = 0; s < 2; ++s) {
             ptx::mbar_init(tfull_bar(s), 1);
-            ptx::mbar_init(tempty_bar(s), 4);
+            ptx::mbar_init(tempty_bar(s), EPI_WARPS);
         }
         ptx::fence_barrier_init();
     }
@@ -221,40 +325,24 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
             }
         }
     } else {
-        // ===================== epilogue (4 warps = 128 accumulator rows) =====================
-        const int quad = warp & 3;              // TMEM lanes [32*quad, 32*quad+32) are the ones this warp may read
-        const int row = quad * 32 + lane;
-        int acc_stage = 0;
-        uint32_t acc_phase = 0;
-        for (long long tile = blockIdx.x; tile < args.total_tiles; tile += gridDim.x) {
-            const TileCoord tc = decode_tile(args, tile);
-            ptx::mbar_wait(tfull_bar(acc_stage), acc_phase);
-            ptx::tc_fence_after();
-            const long long r = (long long)tc.r0 + row;
-            const bool row_ok = row < args.rows_per_tile && r < d.rows_per_group;
-            const long long dst0 = tc.gi * d.out_gstride + d.out_roff + r;
-            const long long res0 = tc.gi * d.res_gstride + d.res_roff + r;
-            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)acc_stage * ACC_STAGE_COLS;
-            const int ncols = min(args.block_n, d.n - tc.n0);
-            for (int c0 = 0; c0 < ncols; c0 += 32) {
-                uint32_t acc[32];
-                const bool two = c0 + 16 < ncols;
-                ptx::tmem_ld16(taddr + (uint32_t)c0, acc);
-                if (two) ptx::tmem_ld16(taddr + (uint32_t)c0 + 16u, acc + 16);
-                ptx::tmem_ld_wait();
-                if (row_ok) {
-                    for (int rep = 0; rep < d.out_rep; ++rep) {
-                        const long long dr = dst0 + (long long)rep * d.out_rep_stride;
-                        const long long rr = res0 + (long long)rep * d.res_rep_stride;
-                        store_chunk16(d, acc, tc.n0 + c0, dr, rr);
-                        if (two) store_chunk16(d, acc + 16, tc.n0 + c0 + 16, dr, rr);
-                    }
-                }
-            }
-            ptx::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(tempty_bar(acc_stage));
-            if (++acc_stage == 2) { acc_stage = 0; acc_phase ^= 1u; }
+        // ===================== epilogue (8 warps: 4 lane quadrants x 2 column halves) =====================
+        float* stage = reinterpret_cast<float*>(smem_raw + (staging_base - ptx::smem_u32(smem_raw))) + (warp - 2) * 32 * 32;
+        const uint32_t tf = tfull_bar(0), te = tempty_bar(0);
+        const bool gelu = d.act == DISTB200_ACT_QUICKGELU;
+        const bool bf_only = d.out && d.out_dtype == DISTB200_BF16 && !d.out2;
+        const bool f_only = d.out && d.out_dtype == DISTB200_F32 && !d.out2;
+        const bool f_and_bf = d.out && d.out_dtype == DISTB200_F32 && d.out2 && d.out2_dtype == DISTB200_BF16;
+        if (bf_only && !d.res && !gelu) epilogue_role<1, false, 0>(args, tmem_base, stage, tf, te, warp, lane);
+        else if (bf_only && !d.res && gelu) epilogue_role<1, false, 1>(args, tmem_base, stage, tf, te, warp, lane);
+        else if (f_only && d.res && !gelu) epilogue_role<0, true, 0>(args, tmem_base, stage, tf, te, warp, lane);
+        else if (f_and_bf && d.res && !gelu) epilogue_role<2, true, 0>(args, tmem_base, stage, tf, te, warp, lane);
+        else if (f_and_bf && d.res && gelu) epilogue_role<2, true, 2>(args, tmem_base, stage, tf, te, warp, lane);
+        else if (d.res) {
+            if (gelu) epilogue_role<3, true, 2>(args, tmem_base, stage, tf, te, warp, lane);
+            else epilogue_role<3, true, 0>(args, tmem_base, stage, tf, te, warp, lane);
+        } else {
+            if (gelu) epilogue_role<3, false, 2>(args, tmem_base, stage, tf, te, warp, lane);
+            else epilogue_role<3, false, 0>(args, tmem_base, stage, tf, te, warp, lane);
         }
     }
 
@@ -389,7 +477,7 @@ int gemm_tcgen05_launch(const distb200_gemm_desc& d, cudaStream_t stream) {
         args.tx_bytes += (uint32_t)(BLOCK_K * args.block_n * 2);
     }
 
-    const int smem = args.stages * (int)stage_bytes + 1024 + 8 * (2 * MAX_STAGES + 4) + 16;
+    const int smem = args.stages * (int)stage_bytes + STAGING_BYTES + 1024 + 8 * (2 * MAX_STAGES + 4) + 16;
     static bool attr_done = false;
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
