@@ -1,14 +1,17 @@
 // Fused softmax attention for the ViT (197 / 257 tokens, head dim 64) on tcgen05 tensor cores.
 //
-// One CTA per (frame, head, 128-query tile); 2 CTAs are co-resident per SM when the keys fit 256 TMEM columns,
-// so one CTA's softmax overlaps the other's loads and MMAs.
-//   warp 4 (one lane)  TMA: Q tile, all K rows and all V rows of the head, straight out of the packed qkv
-//                      activation [frames, tokens, 3*D] (rows past the last token read as zero);
-//                      S = Q K^T   tcgen05.mma SS, fp32 accumulator in TMEM columns [0, keys_pad)
-//                      O = P V     tcgen05.mma TS: A = P read from TMEM, B = V tile used MN-major (no transpose)
-//   warps 0..3         one query row per thread: row max, exp2, row sum in fp32 from tcgen05.ld; the bf16
-//                      probabilities are written back over S with tcgen05.st (S never leaves the SM);
-//                      epilogue scales O by 1/rowsum and stores bf16 [frames, tokens, D].
+// Persistent kernel, one CTA per SM, work item = (frame, head): K and V of the head are loaded once and shared by
+// the item's 128-row query tiles.  Roles:
+//   warp 8  (one lane)  TMA producer: K/V of the next item (2 smem stages) and Q tiles (ring of 4) straight out of
+//                       the packed qkv activation [frames, tokens, 3*D]; rows past the last token read as zero
+//   warp 9  (one lane)  S = Q K^T   tcgen05.mma SS -> fp32 in a TMEM slot (keys_pad columns)
+//   warp 10 (one lane)  O = P V     tcgen05.mma TS: A = P read from TMEM, B = V used MN-major (no transpose)
+//                       (two issuing threads, so that neither product waits behind the other one's barrier)
+//   warps 0-3 / 4-7     two softmax groups, one per TMEM slot (ping-pong): one query row per thread; row max, exp2,
+//                       row sum in fp32 from tcgen05.ld; bf16 probabilities are written back over S with tcgen05.st
+//                       (S and P never leave the SM); epilogue scales O by 1/rowsum and stores bf16.
+// With 257 tokens a slot needs 272 columns and only one fits the 512-column TMEM: group 1 idles and the S MMA,
+// softmax and PV MMA of a tile run back to back (the loads still run ahead).
 #include <cuda.h>
 
 #include "common.cuh"
@@ -21,17 +24,20 @@ int attention_simt_launch(const void* qkv, void* out, int frames, int tokens, in
 namespace {
 
 constexpr int HD = 64;
-constexpr int QT = 128;                 // query rows per CTA
-constexpr int BOX_ROWS = 64;            // rows per TMA box
-constexpr int ATT_THREADS = 160;
+constexpr int QT = 128;                 // query rows per tile
+constexpr int Q_RING = 4;
+constexpr int KV_STAGES = 2;
+constexpr int ATT_THREADS = 352;
+constexpr uint32_t Q_TILE_BYTES = QT * HD * 2;
 
 struct alignas(64) AttArgs {
-    CUtensorMap tm;                     // qkv as (3*D, tokens, frames), box (64, 64, 1), 128B swizzle
+    CUtensorMap tm64;                   // qkv as (3*D, tokens, frames), box (64, 64, 1), 128B swizzle
+    CUtensorMap tm16;                   // same tensor, box (64, 16, 1) for the ragged tail of K / V
     bf16* out;
     int tokens, heads, q_tiles;
     int keys_pad;                       // tokens rounded up to 16
-    int kv_rows;                        // tokens rounded up to BOX_ROWS (smem rows per K / V tile)
-    int tmem_cols, o_col;
+    int slot_cols, o_col, n_slots;
+    long long items;                    // frames * heads
 };
 
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* v) {
@@ -52,141 +58,261 @@ __device__ __forceinline__ void mma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uin
         : "memory");
 }
 
-__global__ void __launch_bounds__(ATT_THREADS) attention_tc_kernel(const __grid_constant__ AttArgs args) {
+__device__ __forceinline__ float fast_exp2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+struct Bars {   // shared-memory addresses of the mbarriers
+    uint32_t kv_full, kv_empty, q_full, q_empty, s_full, p_full, o_full, slot_free;
+};
+
+__global__ void __launch_bounds__(ATT_THREADS, 1) attention_tc_kernel(const __grid_constant__ AttArgs args) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t bars[4];       // load, s_ready, p_ready, o_ready
+    __shared__ __align__(8) uint64_t bar_mem[2 * KV_STAGES + 2 * Q_RING + 8];
     __shared__ uint32_t tmem_slot;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int qt = blockIdx.x % args.q_tiles;
-    const int fh = blockIdx.x / args.q_tiles;
-    const int h = fh % args.heads, f = fh / args.heads;
     const int D = args.heads * HD;
+    const uint32_t kv_bytes = (uint32_t)args.keys_pad * HD * 2;          // one of K / V
+    const uint32_t s_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t s_q = s_base;                                          // Q_RING tiles
+    const uint32_t s_kv = s_q + Q_RING * Q_TILE_BYTES;                    // KV_STAGES x (K | V)
+    Bars b;
+    b.kv_full = ptx::smem_u32(&bar_mem[0]);
+    b.kv_empty = b.kv_full + 8 * KV_STAGES;
+    b.q_full = b.kv_empty + 8 * KV_STAGES;
+    b.q_empty = b.q_full + 8 * Q_RING;
+    b.s_full = b.q_empty + 8 * Q_RING;
+    b.p_full = b.s_full + 16;
+    b.o_full = b.p_full + 16;
+    b.slot_free = b.o_full + 16;
 
-    const uint32_t s_q = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t s_k = s_q + QT * HD * 2;
-    const uint32_t s_v = s_k + (uint32_t)args.kv_rows * HD * 2;
-    const uint32_t bar_load = ptx::smem_u32(&bars[0]), bar_s = ptx::smem_u32(&bars[1]);
-    const uint32_t bar_p = ptx::smem_u32(&bars[2]), bar_o = ptx::smem_u32(&bars[3]);
-
-    if (warp == 4) {
+    if (warp == 9) {
         if (lane == 0) {
-            ptx::prefetch_tensormap(&args.tm);
-            ptx::mbar_init(bar_load, 1);
-            ptx::mbar_init(bar_s, 1);
-            ptx::mbar_init(bar_p, 128);
-            ptx::mbar_init(bar_o, 1);
+            ptx::prefetch_tensormap(&args.tm64);
+            ptx::prefetch_tensormap(&args.tm16);
+            for (int i = 0; i < KV_STAGES; ++i) { ptx::mbar_init(b.kv_full + 8 * i, 1); ptx::mbar_init(b.kv_empty + 8 * i, 1); }
+            for (int i = 0; i < Q_RING; ++i) { ptx::mbar_init(b.q_full + 8 * i, 1); ptx::mbar_init(b.q_empty + 8 * i, 1); }
+            for (int i = 0; i < 2; ++i) {
+                ptx::mbar_init(b.s_full + 8 * i, 1);
+                ptx::mbar_init(b.p_full + 8 * i, 128);
+                ptx::mbar_init(b.o_full + 8 * i, 1);
+                ptx::mbar_init(b.slot_free + 8 * i, 128);
+            }
             ptx::fence_barrier_init();
         }
         __syncwarp();
-        ptx::tmem_alloc(ptx::smem_u32(&tmem_slot), (uint32_t)args.tmem_cols);
+        ptx::tmem_alloc(ptx::smem_u32(&tmem_slot), 512);
         ptx::tmem_relinquish();
     }
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem = tmem_slot;
-    const int q0 = qt * QT;
+    const int QTn = args.q_tiles;
+    const int ns = args.n_slots;
+    long long my_items = (args.items - blockIdx.x + gridDim.x - 1) / gridDim.x;
+    if ((long long)blockIdx.x >= args.items) my_items = 0;
+    const long long total = my_items * QTn;             // tiles of this CTA, g = item_index * q_tiles + qt
 
-    if (warp == 4) {
+    if (warp == 8) {
+        // ===================== TMA producer =====================
         if (lane == 0) {
-            const int kv_boxes = args.kv_rows / BOX_ROWS;
-            const int q_boxes = QT / BOX_ROWS;
-            ptx::mbar_arrive_expect_tx(bar_load, (uint32_t)((q_boxes + 2 * kv_boxes) * BOX_ROWS * HD * 2));
-            for (int i = 0; i < q_boxes; ++i)
-                ptx::tma_load_3d(s_q + i * BOX_ROWS * HD * 2, &args.tm, bar_load, h * HD, q0 + i * BOX_ROWS, f);
-            for (int i = 0; i < kv_boxes; ++i) {
-                ptx::tma_load_3d(s_k + i * BOX_ROWS * HD * 2, &args.tm, bar_load, D + h * HD, i * BOX_ROWS, f);
-                ptx::tma_load_3d(s_v + i * BOX_ROWS * HD * 2, &args.tm, bar_load, 2 * D + h * HD, i * BOX_ROWS, f);
+            const int boxes64 = args.keys_pad / 64, tail16 = (args.keys_pad % 64) / 16;
+            long long g = 0;
+            int it = 0;
+            for (long long item = blockIdx.x; item < args.items; item += gridDim.x, ++it) {
+                const int h = (int)(item % args.heads), f = (int)(item / args.heads);
+                const int st = it % KV_STAGES;
+                const uint32_t ph = (uint32_t)(it / KV_STAGES) & 1u;
+                ptx::mbar_wait(b.kv_empty + 8 * st, ph ^ 1u);
+                ptx::mbar_arrive_expect_tx(b.kv_full + 8 * st, 2 * kv_bytes);
+                const uint32_t sk = s_kv + (uint32_t)st * 2 * kv_bytes, sv = sk + kv_bytes;
+                for (int i = 0; i < boxes64; ++i) {
+                    ptx::tma_load_3d(sk + i * 64 * HD * 2, &args.tm64, b.kv_full + 8 * st, D + h * HD, i * 64, f);
+                    ptx::tma_load_3d(sv + i * 64 * HD * 2, &args.tm64, b.kv_full + 8 * st, 2 * D + h * HD, i * 64, f);
+                }
+                for (int i = 0; i < tail16; ++i) {
+                    const int r = boxes64 * 64 + i * 16;
+                    ptx::tma_load_3d(sk + r * HD * 2, &args.tm16, b.kv_full + 8 * st, D + h * HD, r, f);
+                    ptx::tma_load_3d(sv + r * HD * 2, &args.tm16, b.kv_full + 8 * st, 2 * D + h * HD, r, f);
+                }
+                for (int qt = 0; qt < QTn; ++qt, ++g) {
+                    const int qs = (int)(g % Q_RING);
+                    const uint32_t qph = (uint32_t)(g / Q_RING) & 1u;
+                    ptx::mbar_wait(b.q_empty + 8 * qs, qph ^ 1u);
+                    ptx::mbar_arrive_expect_tx(b.q_full + 8 * qs, Q_TILE_BYTES);
+                    ptx::tma_load_3d(s_q + qs * Q_TILE_BYTES, &args.tm64, b.q_full + 8 * qs, h * HD, qt * QT, f);
+                    ptx::tma_load_3d(s_q + qs * Q_TILE_BYTES + 64 * HD * 2, &args.tm64, b.q_full + 8 * qs, h * HD, qt * QT + 64, f);
+                }
             }
-            ptx::mbar_wait(bar_load, 0);
-            ptx::tc_fence_after();
-            // ---- S = Q K^T : M=128, N=keys_pad (split at 256), K=64 ----
-            const uint64_t dq = ptx::umma_desc_k_sw128(s_q);
-            for (int n0 = 0; n0 < args.keys_pad; n0 += 256) {
-                const int nn = min(256, args.keys_pad - n0);
-                const uint32_t idesc = ptx::umma_idesc_bf16(QT, nn);
-                const uint64_t dk = ptx::umma_desc_k_sw128(s_k + (uint32_t)n0 * HD * 2);
-                for (int ks = 0; ks < HD / 16; ++ks)
-                    ptx::mma_f16_ss(tmem + (uint32_t)n0, dq + (uint64_t)(2 * ks), dk + (uint64_t)(2 * ks), idesc, ks != 0);
-            }
-            ptx::mma_commit(bar_s);
-            // ---- O = P V : A = P in TMEM (bf16 pairs, 8 columns per 16 keys), B = V rows [16ks, 16ks+16) MN-major ----
-            ptx::mbar_wait(bar_p, 0);
-            ptx::tc_fence_after();
-            const uint32_t idesc_pv = ptx::umma_idesc_bf16(QT, HD) | (1u << 16);      // B is MN-major
-            const int ksteps = args.keys_pad / 16;
-            for (int ks = 0; ks < ksteps; ++ks) {
-                const uint64_t dv = ptx::umma_desc_k_sw128(s_v + (uint32_t)ks * 16 * HD * 2);
-                mma_f16_ts(tmem + (uint32_t)args.o_col, tmem + (uint32_t)(8 * ks), dv, idesc_pv, ks != 0);
-            }
-            ptx::mma_commit(bar_o);
         }
-    } else {
-        // ---- softmax: thread = one query row = one TMEM lane ----
-        const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
-        const int row = q0 + warp * 32 + lane;
-        ptx::mbar_wait(bar_s, 0);
-        ptx::tc_fence_after();
-        const float c = 0.125f * 1.4426950408889634f;     // 1/sqrt(64) * log2(e)
-        const int N = args.tokens;
-        float mx = -INFINITY;
-        for (int c0 = 0; c0 < args.keys_pad; c0 += 16) {
-            uint32_t v[16];
-            ptx::tmem_ld16(lane_base + (uint32_t)c0, v);
-            ptx::tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 16; ++i)
-                if (c0 + i < N) mx = fmaxf(mx, __uint_as_float(v[i]));
-        }
-        const float mxs = mx * c;
-        float sum = 0.f;
-        for (int c0 = 0; c0 < args.keys_pad; c0 += 32) {
-            uint32_t v[32];
-            const bool two = c0 + 16 < args.keys_pad;
-            ptx::tmem_ld16(lane_base + (uint32_t)c0, v);
-            if (two) ptx::tmem_ld16(lane_base + (uint32_t)c0 + 16u, v + 16);
-            ptx::tmem_ld_wait();
-            uint32_t p[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const int k0 = c0 + 2 * i;
-                float e0 = (k0 < N && (i < 8 || two)) ? exp2f(fmaf(__uint_as_float(v[2 * i]), c, -mxs)) : 0.f;
-                float e1 = (k0 + 1 < N && (i < 8 || two)) ? exp2f(fmaf(__uint_as_float(v[2 * i + 1]), c, -mxs)) : 0.f;
-                // the row sum must match what the tensor core sees: sum the bf16-rounded probabilities
-                const __nv_bfloat162 pr = __floats2bfloat162_rn(e0, e1);
-                sum += __bfloat162float(pr.x) + __bfloat162float(pr.y);
-                p[i] = *reinterpret_cast<const uint32_t*>(&pr);
+    } else if (warp == 9) {
+        // ===================== S = Q K^T issuer =====================
+        if (lane == 0) {
+            for (long long g = 0; g < total; ++g) {
+                const int it = (int)(g / QTn), qt = (int)(g % QTn);
+                const int st = it % KV_STAGES, qs = (int)(g % Q_RING), slot = (int)(g % ns);
+                if (qt == 0) ptx::mbar_wait(b.kv_full + 8 * st, (uint32_t)(it / KV_STAGES) & 1u);
+                ptx::mbar_wait(b.q_full + 8 * qs, (uint32_t)(g / Q_RING) & 1u);
+                ptx::mbar_wait(b.slot_free + 8 * slot, ((uint32_t)(g / ns) & 1u) ^ 1u);
+                ptx::tc_fence_after();
+                const uint32_t sk = s_kv + (uint32_t)st * 2 * kv_bytes;
+                const uint64_t dq = ptx::umma_desc_k_sw128(s_q + qs * Q_TILE_BYTES);
+                const uint32_t ts = tmem + (uint32_t)(slot * args.slot_cols);
+                for (int n0 = 0; n0 < args.keys_pad; n0 += 256) {
+                    const int nn = min(256, args.keys_pad - n0);
+                    const uint32_t idesc = ptx::umma_idesc_bf16(QT, nn);
+                    const uint64_t dk = ptx::umma_desc_k_sw128(sk + (uint32_t)n0 * HD * 2);
+                    for (int ks = 0; ks < HD / 16; ++ks)
+                        ptx::mma_f16_ss(ts + (uint32_t)n0, dq + (uint64_t)(2 * ks), dk + (uint64_t)(2 * ks), idesc, ks != 0);
+                }
+                ptx::mma_commit(b.s_full + 8 * slot);
+                ptx::mma_commit(b.q_empty + 8 * qs);
             }
-            // P chunk covers keys [c0, c0+32) = 16 packed columns starting at c0/2 (always behind the S read front)
-            tmem_st16(lane_base + (uint32_t)(c0 >> 1), p);
         }
-        ptx::tmem_st_wait();
-        ptx::tc_fence_before();
-        ptx::mbar_arrive(bar_p);
-        // ---- epilogue ----
-        ptx::mbar_wait(bar_o, 0);
-        ptx::tc_fence_after();
-        const float inv = 1.f / sum;
-        uint32_t o[64];
-        ptx::tmem_ld32(lane_base + (uint32_t)args.o_col, o);
-        ptx::tmem_ld32(lane_base + (uint32_t)args.o_col + 32u, o + 32);
-        ptx::tmem_ld_wait();
-        if (row < N) {
-            uint4* dst = reinterpret_cast<uint4*>(args.out + ((long long)f * N + row) * D + h * HD);
+    } else if (warp == 10) {
+        // ===================== O = P V issuer =====================
+        if (lane == 0) {
+            const uint32_t idesc_pv = ptx::umma_idesc_bf16(QT, HD) | (1u << 16);      // B (= V) is MN-major
+            const int ksteps_pv = args.keys_pad / 16;
+            for (long long g = 0; g < total; ++g) {
+                const int it = (int)(g / QTn), qt = (int)(g % QTn);
+                const int st = it % KV_STAGES, slot = (int)(g % ns);
+                ptx::mbar_wait(b.p_full + 8 * slot, (uint32_t)(g / ns) & 1u);
+                ptx::tc_fence_after();
+                const uint32_t sv = s_kv + (uint32_t)st * 2 * kv_bytes + kv_bytes;
+                const uint32_t ts = tmem + (uint32_t)(slot * args.slot_cols);
+                for (int ks = 0; ks < ksteps_pv; ++ks) {
+                    const uint64_t dv = ptx::umma_desc_k_sw128(sv + (uint32_t)ks * 16 * HD * 2);
+                    mma_f16_ts(ts + (uint32_t)args.o_col, ts + (uint32_t)(8 * ks), dv, idesc_pv, ks != 0);
+                }
+                ptx::mma_commit(b.o_full + 8 * slot);
+                if (qt == QTn - 1) ptx::mma_commit(b.kv_empty + 8 * st);        // K and V of the item are no longer needed
+            }
+        }
+    } else if (warp < 8) {
+        // ===================== softmax groups =====================
+        const int grp = warp >> 2;                         // 0 or 1 = TMEM slot
+        const int w4 = warp & 3;
+        if (grp < ns) {
+            const uint32_t ts = tmem + ((uint32_t)(w4 * 32) << 16) + (uint32_t)(grp * args.slot_cols);
+            const float c = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e)
+            const int N = args.tokens;
+            const int full_end = (N / 32) * 32;            // keys [0, full_end) need no validity predicate
+            uint32_t use = 0;
+            for (long long g = grp; g < total; g += ns, ++use) {
+                const long long it = g / QTn;
+                const int qt = (int)(g - it * QTn);
+                const long long item = (long long)blockIdx.x + it * gridDim.x;
+                const int h = (int)(item % args.heads), f = (int)(item / args.heads);
+                const uint32_t ph = use & 1u;
+                const int row = qt * QT + w4 * 32 + lane;
+                const bool warp_has_rows = qt * QT + w4 * 32 < N;
+                ptx::mbar_wait(b.s_full + 8 * grp, ph);
+                ptx::tc_fence_after();
+                float sum = 0.f;
+                if (warp_has_rows) {
+                    // pass 1: row maximum over the valid keys
+                    float mx = -INFINITY;
+                    for (int c0 = 0; c0 < full_end; c0 += 32) {
+                        uint32_t v[32];
+                        ptx::tmem_ld32(ts + (uint32_t)c0, v);
+                        ptx::tmem_ld_wait();
+                        float m0 = __uint_as_float(v[0]), m1 = __uint_as_float(v[1]);
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
-                dst[i] = make_uint4(pack_bf16x2(__uint_as_float(o[8 * i]) * inv, __uint_as_float(o[8 * i + 1]) * inv),
-                                    pack_bf16x2(__uint_as_float(o[8 * i + 2]) * inv, __uint_as_float(o[8 * i + 3]) * inv),
-                                    pack_bf16x2(__uint_as_float(o[8 * i + 4]) * inv, __uint_as_float(o[8 * i + 5]) * inv),
-                                    pack_bf16x2(__uint_as_float(o[8 * i + 6]) * inv, __uint_as_float(o[8 * i + 7]) * inv));
+                        for (int i = 2; i < 32; i += 2) {
+                            m0 = fmaxf(m0, __uint_as_float(v[i]));
+                            m1 = fmaxf(m1, __uint_as_float(v[i + 1]));
+                        }
+                        mx = fmaxf(mx, fmaxf(m0, m1));
+                    }
+                    if (full_end < args.keys_pad) {
+                        uint32_t v[32];
+                        const bool two = full_end + 16 < args.keys_pad;
+                        ptx::tmem_ld16(ts + (uint32_t)full_end, v);
+                        if (two) ptx::tmem_ld16(ts + (uint32_t)full_end + 16u, v + 16);
+                        ptx::tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            if (full_end + i < N && (i < 16 || two)) mx = fmaxf(mx, __uint_as_float(v[i]));
+                    }
+                    // pass 2: p = 2^(s*c - max*c), bf16 pairs written back over S; fp32 row sum
+                    const float mxs = mx * c;
+                    float s0 = 0.f, s1 = 0.f;
+                    for (int c0 = 0; c0 < full_end; c0 += 32) {
+                        uint32_t v[32];
+                        ptx::tmem_ld32(ts + (uint32_t)c0, v);
+                        ptx::tmem_ld_wait();
+                        uint32_t p[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const float e0 = fast_exp2(fmaf(__uint_as_float(v[2 * i]), c, -mxs));
+                            const float e1 = fast_exp2(fmaf(__uint_as_float(v[2 * i + 1]), c, -mxs));
+                            s0 += e0;
+                            s1 += e1;
+                            p[i] = pack_bf16x2(e0, e1);
+                        }
+                        // keys [c0, c0+32) -> 16 packed columns at c0/2: always behind the S read front of this lane
+                        tmem_st16(ts + (uint32_t)(c0 >> 1), p);
+                    }
+                    if (full_end < args.keys_pad) {
+                        uint32_t v[32];
+                        const bool two = full_end + 16 < args.keys_pad;
+                        ptx::tmem_ld16(ts + (uint32_t)full_end, v);
+                        if (two) ptx::tmem_ld16(ts + (uint32_t)full_end + 16u, v + 16);
+                        ptx::tmem_ld_wait();
+                        uint32_t p[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const int k0 = full_end + 2 * i;
+                            const bool in = i < 8 || two;
+                            const float e0 = (in && k0 < N) ? fast_exp2(fmaf(__uint_as_float(v[2 * i]), c, -mxs)) : 0.f;
+                            const float e1 = (in && k0 + 1 < N) ? fast_exp2(fmaf(__uint_as_float(v[2 * i + 1]), c, -mxs)) : 0.f;
+                            s0 += e0;
+                            s1 += e1;
+                            p[i] = pack_bf16x2(e0, e1);
+                        }
+                        tmem_st16(ts + (uint32_t)(full_end >> 1), p);
+                    }
+                    sum = s0 + s1;
+                    ptx::tmem_st_wait();
+                }
+                ptx::tc_fence_before();
+                ptx::mbar_arrive(b.p_full + 8 * grp);
+                ptx::mbar_wait(b.o_full + 8 * grp, ph);
+                ptx::tc_fence_after();
+                if (warp_has_rows) {
+                    const float inv = 1.f / sum;
+                    bf16* dst_row = args.out + ((long long)f * N + row) * D + h * HD;
+#pragma unroll
+                    for (int half = 0; half < 2; ++half) {
+                        uint32_t o[32];
+                        ptx::tmem_ld32(ts + (uint32_t)args.o_col + 32u * half, o);
+                        ptx::tmem_ld_wait();
+                        if (row < N) {
+                            uint4* dst = reinterpret_cast<uint4*>(dst_row + 32 * half);
+#pragma unroll
+                            for (int i = 0; i < 4; ++i)
+                                dst[i] = make_uint4(pack_bf16x2(__uint_as_float(o[8 * i]) * inv, __uint_as_float(o[8 * i + 1]) * inv),
+                                                    pack_bf16x2(__uint_as_float(o[8 * i + 2]) * inv, __uint_as_float(o[8 * i + 3]) * inv),
+                                                    pack_bf16x2(__uint_as_float(o[8 * i + 4]) * inv, __uint_as_float(o[8 * i + 5]) * inv),
+                                                    pack_bf16x2(__uint_as_float(o[8 * i + 6]) * inv, __uint_as_float(o[8 * i + 7]) * inv));
+                        }
+                    }
+                }
+                ptx::tc_fence_before();
+                ptx::mbar_arrive(b.slot_free + 8 * grp);
+            }
         }
     }
     ptx::tc_fence_before();
     __syncthreads();
-    if (warp == 4) {
+    if (warp == 9) {
         ptx::tc_fence_after();
-        ptx::tmem_dealloc(tmem, (uint32_t)args.tmem_cols);
+        ptx::tmem_dealloc(tmem, 512);
     }
 }
 
@@ -198,7 +324,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 
 int attention_tc_launch(const void* qkv, void* out, int frames, int tokens, int heads, cudaStream_t stream) {
     const int keys_pad = (tokens + 15) / 16 * 16;
-    if (keys_pad > 512 - 64 || ((uintptr_t)qkv & 15) || ((uintptr_t)out & 15))
+    if (keys_pad > 288 || ((uintptr_t)qkv & 15) || ((uintptr_t)out & 15))
         return attention_simt_launch(qkv, out, frames, tokens, heads, DISTB200_BF16, stream);
 
     static EncodeTiledFn encode = nullptr;
@@ -213,31 +339,32 @@ int attention_tc_launch(const void* qkv, void* out, int frames, int tokens, int 
     const int D = heads * HD;
     cuuint64_t gdim[3] = {(cuuint64_t)(3 * D), (cuuint64_t)tokens, (cuuint64_t)frames};
     cuuint64_t gstr[2] = {(cuuint64_t)(3 * D) * 2, (cuuint64_t)(3 * D) * 2 * (cuuint64_t)tokens};
-    cuuint32_t box[3] = {HD, BOX_ROWS, 1}, estr[3] = {1, 1, 1};
-    CUresult r = encode(&args.tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(qkv), gdim, gstr, box, estr,
+    cuuint32_t box64[3] = {HD, 64, 1}, box16[3] = {HD, 16, 1}, estr[3] = {1, 1, 1};
+    CUresult r = encode(&args.tm64, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(qkv), gdim, gstr, box64, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    DISTB200_REQUIRE(r == CUDA_SUCCESS, "attention(tcgen05): cuTensorMapEncodeTiled failed with %d", (int)r);
+    r = encode(&args.tm16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(qkv), gdim, gstr, box16, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     DISTB200_REQUIRE(r == CUDA_SUCCESS, "attention(tcgen05): cuTensorMapEncodeTiled failed with %d", (int)r);
     args.out = reinterpret_cast<bf16*>(out);
     args.tokens = tokens;
     args.heads = heads;
     args.q_tiles = (tokens + QT - 1) / QT;
     args.keys_pad = keys_pad;
-    args.kv_rows = (tokens + BOX_ROWS - 1) / BOX_ROWS * BOX_ROWS;
     args.o_col = (keys_pad / 2 + 31) / 32 * 32;
-    int need = args.o_col + HD > keys_pad ? args.o_col + HD : keys_pad;
-    int cols = 32;
-    while (cols < need) cols *= 2;
-    args.tmem_cols = cols;
-    const int smem = QT * HD * 2 + 2 * args.kv_rows * HD * 2 + 1024;
+    args.slot_cols = args.o_col + HD > keys_pad ? args.o_col + HD : keys_pad;
+    args.n_slots = 2 * args.slot_cols <= 512 ? 2 : 1;
+    args.items = (long long)frames * heads;
+    const int smem = Q_RING * (int)Q_TILE_BYTES + KV_STAGES * 2 * keys_pad * HD * 2 + 1024;
     static int smem_set = 0;
     if (smem > smem_set) {
         cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         DISTB200_REQUIRE(e == cudaSuccess, "attention(tcgen05): cannot reserve %d bytes of shared memory: %s", smem, cudaGetErrorString(e));
         smem_set = smem;
     }
-    const long long grid = (long long)frames * heads * args.q_tiles;
-    DISTB200_REQUIRE(grid < 2147483647LL, "attention(tcgen05): grid too large");
+    const long long grid = args.items < sm_count() ? args.items : sm_count();
     attention_tc_kernel<<<(unsigned)grid, ATT_THREADS, smem, stream>>>(args);
     return check_launch("attention_tc");
 }
