@@ -48,7 +48,7 @@ extern "C" int distb200_gemm(const distb200_gemm_desc* desc, void* stream) {
     DISTB200_REQUIRE(d.group_dim == 0 || d.group_dim == 2 || d.group_dim == 3, "gemm: group_dim must be 2 or 3");
     cudaStream_t st = (cudaStream_t)stream;
     if (d.impl == DISTB200_IMPL_SIMT || d.dtype == DISTB200_F32) {
-        DISTB200_REQUIRE(d.impl != DISTB200_IMPL_TCGEN05, "gemm: the tcgen05 kernel needs bf16 operands");
+        DISTB200_REQUIRE(d.impl == DISTB200_IMPL_AUTO || d.impl == DISTB200_IMPL_SIMT, "gemm: the tcgen05 kernels need bf16 operands");
         return gemm_simt_launch(d, st);
     }
     return gemm_tcgen05_launch(d, st);

@@ -16,6 +16,7 @@
 // num_taps x ceil(K/64) k-blocks.  All rows of the 128-row MMA that lie outside the tile are computed on whatever
 // the smem holds and never stored.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "ptx.cuh"
@@ -46,6 +47,7 @@ struct alignas(64) TcArgs {
     int tiles_per_group;
     int n_tiles;
     int group_dim;
+    int ctas;                 // 1, or 2 = CTA pair (cta_group::2): 256 rows x block_n per pair, each CTA holds half of B
     uint32_t b_stage_bytes;
     uint32_t tx_bytes;
     long long total_tiles;
@@ -57,12 +59,14 @@ struct TileCoord {
     int n0;
 };
 
-__device__ __forceinline__ TileCoord decode_tile(const TcArgs& a, long long tile) {
+// tile = index of a unit of work of one CTA (ctas == 1) or of one CTA pair (ctas == 2, tiles_per_group then counts
+// pairs and the CTA of rank r takes the (2 * pair + r)-th row tile of the group, which may lie past the group's end)
+__device__ __forceinline__ TileCoord decode_tile(const TcArgs& a, long long tile, int rank) {
     TileCoord t;
     const int n_idx = (int)(tile % a.n_tiles);
     const long long m_idx = tile / a.n_tiles;
     t.gi = m_idx / a.tiles_per_group;
-    t.r0 = (int)(m_idx % a.tiles_per_group) * a.rows_per_tile;
+    t.r0 = ((int)(m_idx % a.tiles_per_group) * a.ctas + rank) * a.rows_per_tile;
     t.n0 = n_idx * a.block_n;
     return t;
 }
@@ -163,7 +167,7 @@ struct Epi {
 
 template <int OUT, bool RES, int ACT>
 __device__ __forceinline__ void epilogue_role(const TcArgs& args, uint32_t tmem_base, float* stage, uint32_t tfull0, uint32_t tempty0,
-                                              int warp, int lane) {
+                                              int warp, int lane, long long tile0, long long tile_step, int rank) {
     typedef Epi<OUT, RES, ACT> E;
     const distb200_gemm_desc& d = args.d;
     const int quad = warp & 3;              // TMEM lanes [32*quad, 32*quad+32) are the ones this warp may read
@@ -171,8 +175,8 @@ __device__ __forceinline__ void epilogue_role(const TcArgs& args, uint32_t tmem_
     const int sub = lane >> 4, cl = (lane & 15) * 2;
     int acc_stage = 0;
     uint32_t acc_phase = 0;
-    for (long long tile = blockIdx.x; tile < args.total_tiles; tile += gridDim.x) {
-        const TileCoord tc = decode_tile(args, tile);
+    for (long long tile = tile0; tile < args.total_tiles; tile += tile_step) {
+        const TileCoord tc = decode_tile(args, tile, rank);
         const long long rows_left = d.rows_per_group - tc.r0;
         int rows_valid = (int)(rows_left < args.rows_per_tile ? rows_left : (long long)args.rows_per_tile) - quad * 32;
         rows_valid = rows_valid > 32 ? 32 : rows_valid;                 // rows of this quadrant that exist
@@ -213,16 +217,22 @@ __device__ __forceinline__ void epilogue_role(const TcArgs& args, uint32_t tmem_
         }
         ptx::tc_fence_before();
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(tempty0 + 8u * acc_stage);
+        if (lane == 0) {
+            // the accumulator stage is released to the MMA issuer, which lives in the leader CTA of a pair
+            if (rank == 0) ptx::mbar_arrive(tempty0 + 8u * acc_stage);
+            else ptx::mbar_arrive_cluster(ptx::mapa(tempty0 + 8u * acc_stage, 0));
+        }
         if (++acc_stage == 2) { acc_stage = 0; acc_phase ^= 1u; }
     }
 }
 
+template <int CTAS>
 __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __grid_constant__ TcArgs args) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const distb200_gemm_desc& d = args.d;
 
-    // carve shared memory: [stages x (A | B)] [barriers] ; swizzle-128B needs 1024-byte aligned stage bases
+    // carve shared memory: [stages x (A | B)] [epilogue staging] [barriers]; swizzle-128B needs 1024-byte aligned
+    // stage bases.  Both CTAs of a pair use the same offsets (the pair MMA addresses the peer's operands by offset).
     const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t stage_bytes = A_STAGE_BYTES + args.b_stage_bytes;
     const uint32_t staging_base = smem_base + (uint32_t)args.stages * stage_bytes;
@@ -237,26 +247,28 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    const int rank = CTAS == 2 ? (int)ptx::cluster_ctarank() : 0;
+    const long long tile0 = blockIdx.x / CTAS, tile_step = gridDim.x / CTAS;
 
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tensormap(&args.tm_a);
         ptx::prefetch_tensormap(&args.tm_b);
         for (int s = 0; s < args.stages; ++s) {
-            ptx::mbar_init(full_bar(s), 1);
+            ptx::mbar_init(full_bar(s), CTAS);          // pair: the leader's expect_tx arrive + the peer's remote arrive
             ptx::mbar_init(empty_bar(s), 1);
         }
         for (int s = 0; s < 2; ++s) {
             ptx::mbar_init(tfull_bar(s), 1);
-            ptx::mbar_init(tempty_bar(s), EPI_WARPS);
+            ptx::mbar_init(tempty_bar(s), EPI_WARPS * CTAS);
         }
         ptx::fence_barrier_init();
     }
     if (warp == 1) {
-        ptx::tmem_alloc(tmem_slot, TMEM_COLS);
-        ptx::tmem_relinquish();
+        if (CTAS == 2) { ptx::tmem_alloc_2sm(tmem_slot, TMEM_COLS); ptx::tmem_relinquish_2sm(); }
+        else { ptx::tmem_alloc(tmem_slot, TMEM_COLS); ptx::tmem_relinquish(); }
     }
     ptx::tc_fence_before();
-    __syncthreads();
+    if (CTAS == 2) ptx::cluster_sync(); else __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
 
@@ -267,13 +279,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (long long tile = blockIdx.x; tile < args.total_tiles; tile += gridDim.x) {
-                const TileCoord tc = decode_tile(args, tile);
+            const int b_rows = args.block_n / CTAS;     // a pair splits the B tile: rank r holds rows [r * block_n / 2, ...)
+            for (long long tile = tile0; tile < args.total_tiles; tile += tile_step) {
+                const TileCoord tc = decode_tile(args, tile, rank);
                 for (int it = 0; it < iters; ++it) {
                     const int tap = it / args.k_blocks;
                     const int kb = it - tap * args.k_blocks;
                     ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
-                    ptx::mbar_arrive_expect_tx(full_bar(stage), args.tx_bytes);
                     const uint32_t sa = smem_base + (uint32_t)stage * stage_bytes;
                     const uint32_t sb = sa + A_STAGE_BYTES;
                     int c1, c2, c3;
@@ -286,21 +298,31 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
                         c2 = d.tap_off[tap][1] + (args.group_dim == 3 ? 0 : (int)tc.gi);
                         c3 = d.tap_off[tap][2] + (args.group_dim == 3 ? (int)tc.gi : 0);
                     }
-                    ptx::tma_load_4d(sa, &args.tm_a, full_bar(stage), kb * BLOCK_K, c1, c2, c3);
-                    ptx::tma_load_3d(sb, &args.tm_b, full_bar(stage), kb * BLOCK_K, tc.n0, tap);
+                    if (CTAS == 2) {
+                        // all bytes of the pair are counted on the leader's barrier, where the MMA issuer waits
+                        const uint32_t lead_full = ptx::mapa(full_bar(stage), 0);
+                        if (rank == 0) ptx::mbar_arrive_expect_tx(full_bar(stage), 2 * args.tx_bytes);
+                        else ptx::mbar_arrive_cluster(lead_full);
+                        ptx::tma_load_4d_2sm(sa, &args.tm_a, lead_full, kb * BLOCK_K, c1, c2, c3);
+                        ptx::tma_load_3d_2sm(sb, &args.tm_b, lead_full, kb * BLOCK_K, tc.n0 + rank * b_rows, tap);
+                    } else {
+                        ptx::mbar_arrive_expect_tx(full_bar(stage), args.tx_bytes);
+                        ptx::tma_load_4d(sa, &args.tm_a, full_bar(stage), kb * BLOCK_K, c1, c2, c3);
+                        ptx::tma_load_3d(sb, &args.tm_b, full_bar(stage), kb * BLOCK_K, tc.n0, tap);
+                    }
                     if (++stage == args.stages) { stage = 0; phase ^= 1u; }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
-            const uint32_t idesc = ptx::umma_idesc_bf16(BLOCK_M, args.block_n);
+        // ===================== MMA issuer (leader CTA of a pair only) =====================
+        if (lane == 0 && rank == 0) {
+            const uint32_t idesc = ptx::umma_idesc_bf16(BLOCK_M * CTAS, args.block_n);
             int stage = 0;
             uint32_t phase = 0;
             int acc_stage = 0;
             uint32_t acc_phase = 0;
-            for (long long tile = blockIdx.x; tile < args.total_tiles; tile += gridDim.x) {
+            for (long long tile = tile0; tile < args.total_tiles; tile += tile_step) {
                 ptx::mbar_wait(tempty_bar(acc_stage), acc_phase ^ 1u);
                 ptx::tc_fence_after();
                 const uint32_t tmem_d = tmem_base + (uint32_t)acc_stage * ACC_STAGE_COLS;
@@ -315,12 +337,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
                     ksteps = ksteps > BLOCK_K / 16 ? BLOCK_K / 16 : ksteps;
                     for (int ks = 0; ks < ksteps; ++ks) {
                         // advancing 16 bf16 (32 bytes) along K inside the swizzle row: +2 in the (addr >> 4) field
-                        ptx::mma_f16_ss(tmem_d, da + (uint64_t)(2 * ks), db + (uint64_t)(2 * ks), idesc, (it | ks) != 0);
+                        if (CTAS == 2) ptx::mma_f16_ss_2sm(tmem_d, da + (uint64_t)(2 * ks), db + (uint64_t)(2 * ks), idesc, (it | ks) != 0);
+                        else ptx::mma_f16_ss(tmem_d, da + (uint64_t)(2 * ks), db + (uint64_t)(2 * ks), idesc, (it | ks) != 0);
                     }
-                    ptx::mma_commit(empty_bar(stage));
+                    if (CTAS == 2) ptx::mma_commit_2sm(empty_bar(stage), 3);    // frees the stage in both CTAs
+                    else ptx::mma_commit(empty_bar(stage));
                     if (++stage == args.stages) { stage = 0; phase ^= 1u; }
                 }
-                ptx::mma_commit(tfull_bar(acc_stage));
+                if (CTAS == 2) ptx::mma_commit_2sm(tfull_bar(acc_stage), 3);    // both CTAs' epilogues may start
+                else ptx::mma_commit(tfull_bar(acc_stage));
                 if (++acc_stage == 2) { acc_stage = 0; acc_phase ^= 1u; }
             }
         }
@@ -332,25 +357,28 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
         const bool bf_only = d.out && d.out_dtype == DISTB200_BF16 && !d.out2;
         const bool f_only = d.out && d.out_dtype == DISTB200_F32 && !d.out2;
         const bool f_and_bf = d.out && d.out_dtype == DISTB200_F32 && d.out2 && d.out2_dtype == DISTB200_BF16;
-        if (bf_only && !d.res && !gelu) epilogue_role<1, false, 0>(args, tmem_base, stage, tf, te, warp, lane);
-        else if (bf_only && !d.res && gelu) epilogue_role<1, false, 1>(args, tmem_base, stage, tf, te, warp, lane);
-        else if (f_only && d.res && !gelu) epilogue_role<0, true, 0>(args, tmem_base, stage, tf, te, warp, lane);
-        else if (f_and_bf && d.res && !gelu) epilogue_role<2, true, 0>(args, tmem_base, stage, tf, te, warp, lane);
-        else if (f_and_bf && d.res && gelu) epilogue_role<2, true, 2>(args, tmem_base, stage, tf, te, warp, lane);
+#define DISTB200_EPI(OUT, RES, ACT) epilogue_role<OUT, RES, ACT>(args, tmem_base, stage, tf, te, warp, lane, tile0, tile_step, rank)
+        if (bf_only && !d.res && !gelu) DISTB200_EPI(1, false, 0);
+        else if (bf_only && !d.res && gelu) DISTB200_EPI(1, false, 1);
+        else if (f_only && d.res && !gelu) DISTB200_EPI(0, true, 0);
+        else if (f_and_bf && d.res && !gelu) DISTB200_EPI(2, true, 0);
+        else if (f_and_bf && d.res && gelu) DISTB200_EPI(2, true, 2);
         else if (d.res) {
-            if (gelu) epilogue_role<3, true, 2>(args, tmem_base, stage, tf, te, warp, lane);
-            else epilogue_role<3, true, 0>(args, tmem_base, stage, tf, te, warp, lane);
+            if (gelu) DISTB200_EPI(3, true, 2);
+            else DISTB200_EPI(3, true, 0);
         } else {
-            if (gelu) epilogue_role<3, false, 2>(args, tmem_base, stage, tf, te, warp, lane);
-            else epilogue_role<3, false, 0>(args, tmem_base, stage, tf, te, warp, lane);
+            if (gelu) DISTB200_EPI(3, false, 2);
+            else DISTB200_EPI(3, false, 0);
         }
+#undef DISTB200_EPI
     }
 
     ptx::tc_fence_before();
-    __syncthreads();
+    if (CTAS == 2) ptx::cluster_sync(); else __syncthreads();      // nobody leaves while the peer may still address this CTA
     if (warp == 1) {
         ptx::tc_fence_after();
-        ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+        if (CTAS == 2) ptx::tmem_dealloc_2sm(tmem_base, TMEM_COLS);
+        else ptx::tmem_dealloc(tmem_base, TMEM_COLS);
     }
 }
 
@@ -445,10 +473,19 @@ int gemm_tcgen05_launch(const distb200_gemm_desc& d, cudaStream_t stream) {
     } else {
         args.rows_per_tile = BLOCK_M;
     }
-    args.tiles_per_group = (int)((d.rows_per_group + args.rows_per_tile - 1) / args.rows_per_tile);
+    const int row_tiles = (int)((d.rows_per_group + args.rows_per_tile - 1) / args.rows_per_tile);
     args.n_tiles = (d.n + args.block_n - 1) / args.block_n;
+    // CTA pairs (cta_group::2) halve the L2 -> SM traffic of B; they need an even split of the B tile and enough tiles
+    static const int ctas_env = getenv("DISTB200_GEMM_CTAS") ? atoi(getenv("DISTB200_GEMM_CTAS")) : 2;
+    args.ctas = (ctas_env == 2 && args.block_n % 32 == 0 && d.groups * row_tiles * args.n_tiles >= 2 * sm_count()) ? 2 : 1;
+    if (d.impl == DISTB200_IMPL_TCGEN05_1CTA) args.ctas = 1;
+    if (d.impl == DISTB200_IMPL_TCGEN05_2CTA) {
+        DISTB200_REQUIRE(args.block_n % 32 == 0, "gemm(tcgen05): CTA pairs need block_n %% 32 == 0 (block_n=%d)", args.block_n);
+        args.ctas = 2;
+    }
+    args.tiles_per_group = (row_tiles + args.ctas - 1) / args.ctas;
     args.total_tiles = d.groups * args.tiles_per_group * args.n_tiles;
-    args.b_stage_bytes = (uint32_t)args.block_n * BLOCK_K * 2;
+    args.b_stage_bytes = (uint32_t)(args.block_n / args.ctas) * BLOCK_K * 2;
     const uint32_t stage_bytes = A_STAGE_BYTES + args.b_stage_bytes;
     args.stages = SMEM_BUDGET / (int)stage_bytes;
     if (args.stages > MAX_STAGES) args.stages = MAX_STAGES;
@@ -472,20 +509,39 @@ int gemm_tcgen05_launch(const distb200_gemm_desc& d, cudaStream_t stream) {
     {
         long long dims[3] = {d.k, d.n, d.num_taps};
         long long str[3] = {1, d.ldb, d.num_taps > 1 ? d.b_tap_stride : d.ldb * d.n};
-        int box[3] = {BLOCK_K, args.block_n, 1};
+        int box[3] = {BLOCK_K, args.block_n / args.ctas, 1};
         if (make_map(&args.tm_b, d.b, 3, dims, str, box, "B")) return 1;
-        args.tx_bytes += (uint32_t)(BLOCK_K * args.block_n * 2);
+        args.tx_bytes += (uint32_t)(BLOCK_K * (args.block_n / args.ctas) * 2);
     }
 
     const int smem = args.stages * (int)stage_bytes + STAGING_BYTES + 1024 + 8 * (2 * MAX_STAGES + 4) + 16;
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tcgen05_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         DISTB200_REQUIRE(e == cudaSuccess, "gemm(tcgen05): cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
         attr_done = true;
     }
-    long long grid = args.total_tiles < sm_count() ? args.total_tiles : sm_count();
-    gemm_tcgen05_kernel<<<(unsigned)grid, NUM_THREADS, smem, stream>>>(args);
+    if (args.ctas == 2) {
+        long long clusters = args.total_tiles < sm_count() / 2 ? args.total_tiles : sm_count() / 2;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(2 * clusters));
+        cfg.blockDim = dim3(NUM_THREADS);
+        cfg.dynamicSmemBytes = (size_t)smem;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<2>, args);
+        DISTB200_REQUIRE(e == cudaSuccess, "gemm(tcgen05): cluster launch failed: %s", cudaGetErrorString(e));
+    } else {
+        long long grid = args.total_tiles < sm_count() ? args.total_tiles : sm_count();
+        gemm_tcgen05_kernel<1><<<(unsigned)grid, NUM_THREADS, smem, stream>>>(args);
+    }
     return check_launch("gemm_tcgen05");
 }
 

@@ -15,7 +15,7 @@ from . import build as _build
 
 F32, BF16 = 0, 1
 ACT_NONE, ACT_QUICKGELU = 0, 1
-IMPL_AUTO, IMPL_SIMT, IMPL_TCGEN05 = 0, 1, 2
+IMPL_AUTO, IMPL_SIMT, IMPL_TCGEN05, IMPL_TCGEN05_1CTA, IMPL_TCGEN05_2CTA = 0, 1, 2, 3, 4
 MAX_TAPS = 9
 
 _TORCH2ENUM = {torch.float32: F32, torch.bfloat16: BF16}

@@ -31,7 +31,8 @@ extern "C" {
 
 enum { DISTB200_F32 = 0, DISTB200_BF16 = 1 };
 enum { DISTB200_ACT_NONE = 0, DISTB200_ACT_QUICKGELU = 1 };   /* x * sigmoid(1.702 x), clip.py:199-201 */
-enum { DISTB200_IMPL_AUTO = 0, DISTB200_IMPL_SIMT = 1, DISTB200_IMPL_TCGEN05 = 2 };
+enum { DISTB200_IMPL_AUTO = 0, DISTB200_IMPL_SIMT = 1, DISTB200_IMPL_TCGEN05 = 2,
+       DISTB200_IMPL_TCGEN05_1CTA = 3, DISTB200_IMPL_TCGEN05_2CTA = 4 };   /* 3 / 4 force single-CTA / CTA-pair (cta_group::2) tiles */
 
 int         distb200_version(void);
 int         distb200_arch(void);          /* 100 : compiled for sm_100a only */

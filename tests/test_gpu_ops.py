@@ -104,14 +104,14 @@ def _call(ops, sc, a, b, bias, res, out, out2, use_bias, use_res, act, impl):
 
 
 @pytest.mark.parametrize("name", list(SCENARIOS))
-@pytest.mark.parametrize("mode", ["simt_fp32", "simt_bf16", "tcgen05"])
+@pytest.mark.parametrize("mode", ["simt_fp32", "simt_bf16", "tcgen05", "tcgen05_pair"])
 def test_gemm(name, mode):
     ops = _ops()
     sc = SCENARIOS[name]
     dtype = torch.float32 if mode == "simt_fp32" else torch.bfloat16
-    impl = ops.IMPL_TCGEN05 if mode == "tcgen05" else ops.IMPL_SIMT
-    if mode == "tcgen05" and sc["n"] % 16:
-        pytest.skip("tcgen05 path needs n % 16 == 0")
+    impl = {"tcgen05": ops.IMPL_TCGEN05_1CTA, "tcgen05_pair": ops.IMPL_TCGEN05_2CTA}.get(mode, ops.IMPL_SIMT)
+    if mode.startswith("tcgen05") and sc["n"] % (32 if mode == "tcgen05_pair" else 16):
+        pytest.skip("tcgen05 path needs n % 16 == 0 (n % 32 for CTA pairs)")
     a, b, bias, res = _build(sc, dtype)
     out_rows = sc.get("out_rows", sc["groups"] * sc["rpg"])
     for use_bias, use_res, act in [(False, False, False), (True, True, True), (True, False, True), (True, True, False)]:
