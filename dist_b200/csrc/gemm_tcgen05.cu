@@ -254,7 +254,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
         ptx::prefetch_tensormap(&args.tm_a);
         ptx::prefetch_tensormap(&args.tm_b);
         for (int s = 0; s < args.stages; ++s) {
-            ptx::mbar_init(full_bar(s), CTAS);          // pair: the leader's expect_tx arrive + the peer's remote arrive
+            ptx::mbar_init(full_bar(s), 1);
             ptx::mbar_init(empty_bar(s), 1);
         }
         for (int s = 0; s < 2; ++s) {
@@ -276,7 +276,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
 
     if (warp == 0) {
         // ===================== TMA producer =====================
-        if (lane == 0) {
+        // The whole warp runs the loop (warp-uniform control flow keeps addresses and coordinates in uniform
+        // registers); one elected lane issues the asynchronous operations.
+        {
             int stage = 0;
             uint32_t phase = 0;
             const int b_rows = args.block_n / CTAS;     // a pair splits the B tile: rank r holds rows [r * block_n / 2, ...)
@@ -299,24 +301,29 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
                         c3 = d.tap_off[tap][2] + (args.group_dim == 3 ? (int)tc.gi : 0);
                     }
                     if (CTAS == 2) {
-                        // all bytes of the pair are counted on the leader's barrier, where the MMA issuer waits
+                        // All bytes of the pair are counted on the leader's barrier, where the MMA issuer waits.  The peer
+                        // needs no arrive of its own: it can only refill a stage after the leader's MMAs released it
+                        // (multicast commit below), i.e. after the barrier's previous phase completed.
                         const uint32_t lead_full = ptx::mapa(full_bar(stage), 0);
-                        if (rank == 0) ptx::mbar_arrive_expect_tx(full_bar(stage), 2 * args.tx_bytes);
-                        else ptx::mbar_arrive_cluster(lead_full);
-                        ptx::tma_load_4d_2sm(sa, &args.tm_a, lead_full, kb * BLOCK_K, c1, c2, c3);
-                        ptx::tma_load_3d_2sm(sb, &args.tm_b, lead_full, kb * BLOCK_K, tc.n0 + rank * b_rows, tap);
-                    } else {
+                        if (ptx::elect_one()) {
+                            if (rank == 0) ptx::mbar_arrive_expect_tx(full_bar(stage), 2 * args.tx_bytes);
+                            ptx::tma_load_4d_2sm(sa, &args.tm_a, lead_full, kb * BLOCK_K, c1, c2, c3);
+                            ptx::tma_load_3d_2sm(sb, &args.tm_b, lead_full, kb * BLOCK_K, tc.n0 + rank * b_rows, tap);
+                        }
+                    } else if (ptx::elect_one()) {
                         ptx::mbar_arrive_expect_tx(full_bar(stage), args.tx_bytes);
                         ptx::tma_load_4d(sa, &args.tm_a, full_bar(stage), kb * BLOCK_K, c1, c2, c3);
                         ptx::tma_load_3d(sb, &args.tm_b, full_bar(stage), kb * BLOCK_K, tc.n0, tap);
                     }
+                    __syncwarp();
                     if (++stage == args.stages) { stage = 0; phase ^= 1u; }
                 }
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer (leader CTA of a pair only) =====================
-        if (lane == 0 && rank == 0) {
+        // Whole warp in the loop, one elected lane issues tcgen05.mma / tcgen05.commit (see the producer).
+        if (rank == 0) {
             const uint32_t idesc = ptx::umma_idesc_bf16(BLOCK_M * CTAS, args.block_n);
             int stage = 0;
             uint32_t phase = 0;
@@ -335,17 +342,23 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
                     const uint64_t db = ptx::umma_desc_k_sw128(sa + A_STAGE_BYTES);
                     int ksteps = (d.k - kb * BLOCK_K + 15) / 16;
                     ksteps = ksteps > BLOCK_K / 16 ? BLOCK_K / 16 : ksteps;
-                    for (int ks = 0; ks < ksteps; ++ks) {
-                        // advancing 16 bf16 (32 bytes) along K inside the swizzle row: +2 in the (addr >> 4) field
-                        if (CTAS == 2) ptx::mma_f16_ss_2sm(tmem_d, da + (uint64_t)(2 * ks), db + (uint64_t)(2 * ks), idesc, (it | ks) != 0);
-                        else ptx::mma_f16_ss(tmem_d, da + (uint64_t)(2 * ks), db + (uint64_t)(2 * ks), idesc, (it | ks) != 0);
+                    if (ptx::elect_one()) {
+                        for (int ks = 0; ks < ksteps; ++ks) {
+                            // advancing 16 bf16 (32 bytes) along K inside the swizzle row: +2 in the (addr >> 4) field
+                            if (CTAS == 2) ptx::mma_f16_ss_2sm(tmem_d, da + (uint64_t)(2 * ks), db + (uint64_t)(2 * ks), idesc, (it | ks) != 0);
+                            else ptx::mma_f16_ss(tmem_d, da + (uint64_t)(2 * ks), db + (uint64_t)(2 * ks), idesc, (it | ks) != 0);
+                        }
+                        if (CTAS == 2) ptx::mma_commit_2sm(empty_bar(stage), 3);    // frees the stage in both CTAs
+                        else ptx::mma_commit(empty_bar(stage));
                     }
-                    if (CTAS == 2) ptx::mma_commit_2sm(empty_bar(stage), 3);    // frees the stage in both CTAs
-                    else ptx::mma_commit(empty_bar(stage));
+                    __syncwarp();
                     if (++stage == args.stages) { stage = 0; phase ^= 1u; }
                 }
-                if (CTAS == 2) ptx::mma_commit_2sm(tfull_bar(acc_stage), 3);    // both CTAs' epilogues may start
-                else ptx::mma_commit(tfull_bar(acc_stage));
+                if (ptx::elect_one()) {
+                    if (CTAS == 2) ptx::mma_commit_2sm(tfull_bar(acc_stage), 3);    // both CTAs' epilogues may start
+                    else ptx::mma_commit(tfull_bar(acc_stage));
+                }
+                __syncwarp();
                 if (++acc_stage == 2) { acc_stage = 0; acc_phase ^= 1u; }
             }
         }

@@ -112,8 +112,10 @@ __device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
     return r;
 }
+// (default .release.cta semantics, as CUTLASS' ClusterBarrier::arrive(cta_id): an explicit .release.cluster costs a
+//  GPU-scope MEMBAR + ERRBAR per arrive)
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA loads of a CTA pair: data lands in the issuing CTA's shared memory, the bytes are counted on the barrier at
 // `bar` (a shared::cluster address, normally the leader CTA's)
