@@ -23,22 +23,26 @@ __device__ __forceinline__ void ln_store4<bf16>(bf16* y, int c, float4 v) {
     *reinterpret_cast<uint2*>(y + c) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
 }
 
-template <typename OutT>
+// LPR lanes cooperate on one row (32 for wide rows; 8 for rows of <= 128 floats such as the Ct = 96 temporal
+// stream, so that a warp covers 4 rows and no lane idles); each lane holds up to LN_MAXV float4 of its row.
+template <typename OutT, int LPR>
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ in1, long long ld_in1,
                                                         const float* __restrict__ in2, long long ld_in2, long long in2_period,
                                                         long long rows, int cols, float eps,
                                                         const float* __restrict__ g1, const float* __restrict__ b1, OutT* y1, long long ld_y1,
                                                         const float* __restrict__ g2, const float* __restrict__ b2, OutT* y2, long long ld_y2) {
-    const int lane = threadIdx.x & 31;
-    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (row >= rows) return;
-    const float* x = in1 + row * ld_in1;
-    const float* x2 = in2 ? in2 + (row % in2_period) * ld_in2 : nullptr;
-    float4 v[LN_MAXV];
+    constexpr int RPW = 32 / LPR;                       // rows per warp
+    constexpr int MAXV = LPR == 32 ? LN_MAXV : 4;
+    const int lane = threadIdx.x & 31, sub = lane % LPR;
+    const long long row = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW + lane / LPR;
+    const bool row_ok = row < rows;
+    const float* x = in1 + (row_ok ? row : 0) * ld_in1;
+    const float* x2 = in2 ? in2 + ((row_ok ? row : 0) % in2_period) * ld_in2 : nullptr;
+    float4 v[MAXV];
     float sum = 0.f;
 #pragma unroll
-    for (int i = 0; i < LN_MAXV; ++i) {
-        const int c = (i * 32 + lane) * 4;
+    for (int i = 0; i < MAXV; ++i) {
+        const int c = (i * LPR + sub) * 4;
         if (c < cols) {
             v[i] = *reinterpret_cast<const float4*>(x + c);
             if (x2) {
@@ -48,20 +52,25 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
             sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
         }
     }
-    const float mean = warp_sum(sum) / (float)cols;
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum / (float)cols;
     float sq = 0.f;
 #pragma unroll
-    for (int i = 0; i < LN_MAXV; ++i) {
-        const int c = (i * 32 + lane) * 4;
+    for (int i = 0; i < MAXV; ++i) {
+        const int c = (i * LPR + sub) * 4;
         if (c < cols) {
             const float a = v[i].x - mean, b = v[i].y - mean, cc = v[i].z - mean, dd = v[i].w - mean;
             sq += (a * a + b * b) + (cc * cc + dd * dd);
         }
     }
-    const float rstd = rsqrtf(warp_sum(sq) / (float)cols + eps);
 #pragma unroll
-    for (int i = 0; i < LN_MAXV; ++i) {
-        const int c = (i * 32 + lane) * 4;
+    for (int o = LPR / 2; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    const float rstd = rsqrtf(sq / (float)cols + eps);
+    if (!row_ok) return;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+        const int c = (i * LPR + sub) * 4;
         if (c < cols) {
             float4 n;
             n.x = (v[i].x - mean) * rstd; n.y = (v[i].y - mean) * rstd;
@@ -77,29 +86,40 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
 }
 
 // ---------------------------------------------------------------------------------------------------
-// patchify: one thread per pixel pair; reads are contiguous along image rows, writes are 2*esize contiguous.
+// patchify: one group of TPR threads per image row (clip, frame, channel, y); VEC pixels per thread.  Reads are
+// contiguous along the row, writes are VEC*esize contiguous pieces of the patch rows; index arithmetic once per row.
 // ---------------------------------------------------------------------------------------------------
-template <typename OutT>
+template <typename OutT, int VEC>
+__device__ __forceinline__ void store_pixels(OutT* o, const float* px);
+template <> __device__ __forceinline__ void store_pixels<float, 4>(float* o, const float* px) { *reinterpret_cast<float4*>(o) = make_float4(px[0], px[1], px[2], px[3]); }
+template <> __device__ __forceinline__ void store_pixels<float, 2>(float* o, const float* px) { *reinterpret_cast<float2*>(o) = make_float2(px[0], px[1]); }
+template <> __device__ __forceinline__ void store_pixels<bf16, 4>(bf16* o, const float* px) { *reinterpret_cast<uint2*>(o) = make_uint2(pack_bf16x2(px[0], px[1]), pack_bf16x2(px[2], px[3])); }
+template <> __device__ __forceinline__ void store_pixels<bf16, 2>(bf16* o, const float* px) { *reinterpret_cast<uint32_t*>(o) = pack_bf16x2(px[0], px[1]); }
+
+template <typename OutT, int VEC, int TPR>
 __global__ void __launch_bounds__(256) patchify_kernel(const float* __restrict__ video, OutT* __restrict__ out, int clips, int T, int H, int W,
                                                        int p, int first, int step, int n_sel, long long ld_out) {
+    constexpr int RPB = 256 / TPR;                      // image rows per block
     const int g = W / p;
-    const int halfW = W >> 1;
-    const long long total = (long long)clips * n_sel * 3 * H * halfW;
-    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-        const int xh = (int)(idx % halfW);
-        long long rest = idx / halfW;
+    const long long n_rows = (long long)clips * n_sel * 3 * H;
+    const int tx = threadIdx.x % TPR;
+    for (long long row = (long long)blockIdx.x * RPB + threadIdx.x / TPR; row < n_rows; row += (long long)gridDim.x * RPB) {
+        long long rest = row;
         const int y = (int)(rest % H); rest /= H;
         const int c = (int)(rest % 3); rest /= 3;
         const int i = (int)(rest % n_sel);
         const int clip = (int)(rest / n_sel);
-        const int x = xh * 2;
         const int frame = first + i * step;
-        const float2 px = *reinterpret_cast<const float2*>(video + ((((long long)clip * 3 + c) * T + frame) * H + y) * W + x);
-        const int pr = y / p, iy = y - pr * p, pc = x / p, ix = x - pc * p;
-        const long long orow = ((long long)clip * n_sel + i) * (g * g) + pr * g + pc;
-        OutT* o = out + orow * ld_out + (c * p + iy) * p + ix;
-        o[0] = from_float<OutT>(px.x);
-        o[1] = from_float<OutT>(px.y);
+        const float* src = video + ((((long long)clip * 3 + c) * T + frame) * H + y) * W;
+        const int pr = y / p, iy = y - pr * p;
+        OutT* dst = out + (((long long)clip * n_sel + i) * (g * g) + (long long)pr * g) * ld_out + (c * p + iy) * p;
+        for (int x = tx * VEC; x < W; x += TPR * VEC) {
+            float px[VEC];
+            if (VEC == 4) *reinterpret_cast<float4*>(px) = *reinterpret_cast<const float4*>(src + x);
+            else *reinterpret_cast<float2*>(px) = *reinterpret_cast<const float2*>(src + x);
+            const int pc = x / p, ix = x - pc * p;
+            store_pixels<OutT, VEC>(dst + (long long)pc * ld_out + ix, px);
+        }
     }
 }
 
@@ -137,8 +157,28 @@ __global__ void mean_rows_kernel(const float* __restrict__ src, long long row_st
 }
 
 // ---------------------------------------------------------------------------------------------------
-// single-query cross attention: one warp per (batch element, head); head dim 64 = 2 dims per lane.
+// single-query cross attention: one warp per (batch element, head), head dim 64.
+//   scores: one key per lane (the lane reads its whole 64-wide key row: full 128 B lines, 64 independent FMAs),
+//   softmax over the lanes' scores, then P.V with two dims per lane and four keys in flight.
 // ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void load_row64(const float* p, float* v) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) *reinterpret_cast<float4*>(v + 4 * i) = *reinterpret_cast<const float4*>(p + 4 * i);
+}
+__device__ __forceinline__ void load_row64(const bf16* p, float* v) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const uint4 u = *reinterpret_cast<const uint4*>(p + 8 * i);
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[j]));
+            v[8 * i + 2 * j] = f.x;
+            v[8 * i + 2 * j + 1] = f.y;
+        }
+    }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(128) cross_attention_kernel(const T* __restrict__ q, const T* __restrict__ kv, T* __restrict__ out,
                                                               int batch, int keys, int heads) {
@@ -150,18 +190,24 @@ __global__ void __launch_bounds__(128) cross_attention_kernel(const T* __restric
     float* sc = sc_all + (size_t)warp * keys;
     const int b = (int)(item / heads), h = (int)(item % heads);
     const int C = heads * 64;
-    const float q0 = to_float(q[(long long)b * C + h * 64 + lane * 2]) * 0.125f;
-    const float q1 = to_float(q[(long long)b * C + h * 64 + lane * 2 + 1]) * 0.125f;
-    const T* kbase = kv + (long long)b * keys * 2 * C + h * 64 + lane * 2;
+    float qv[64];
+    load_row64(q + (long long)b * C + h * 64, qv);
+    const T* kbase = kv + (long long)b * keys * 2 * C + h * 64;
     float mx = -INFINITY;
-    for (int j = 0; j < keys; ++j) {
-        const T* kp = kbase + (long long)j * 2 * C;
-        float s = q0 * to_float(kp[0]) + q1 * to_float(kp[1]);
-        s = warp_sum(s);
-        if (lane == 0) sc[j] = s;
+    for (int j = lane; j < keys; j += 32) {
+        float kr[64];
+        load_row64(kbase + (long long)j * 2 * C, kr);
+        float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 64; i += 2) {
+            s0 = fmaf(qv[i], kr[i], s0);
+            s1 = fmaf(qv[i + 1], kr[i + 1], s1);
+        }
+        const float s = (s0 + s1) * 0.125f;
+        sc[j] = s;
         mx = fmaxf(mx, s);
     }
-    __syncwarp();
+    mx = warp_max(mx);
     float den = 0.f;
     for (int j = lane; j < keys; j += 32) {
         const float e = __expf(sc[j] - mx);
@@ -170,17 +216,26 @@ __global__ void __launch_bounds__(128) cross_attention_kernel(const T* __restric
     }
     den = warp_sum(den);
     __syncwarp();
-    float o0 = 0.f, o1 = 0.f;
-    const T* vbase = kbase + C;
-    for (int j = 0; j < keys; ++j) {
+    float o0[4] = {0.f, 0.f, 0.f, 0.f}, o1[4] = {0.f, 0.f, 0.f, 0.f};
+    const T* vbase = kbase + C + lane * 2;
+    int j = 0;
+    for (; j + 4 <= keys; j += 4) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const T* vp = vbase + (long long)(j + u) * 2 * C;
+            const float pj = sc[j + u];
+            o0[u] = fmaf(pj, to_float(vp[0]), o0[u]);
+            o1[u] = fmaf(pj, to_float(vp[1]), o1[u]);
+        }
+    }
+    for (; j < keys; ++j) {
         const T* vp = vbase + (long long)j * 2 * C;
-        const float pj = sc[j];
-        o0 = fmaf(pj, to_float(vp[0]), o0);
-        o1 = fmaf(pj, to_float(vp[1]), o1);
+        o0[0] = fmaf(sc[j], to_float(vp[0]), o0[0]);
+        o1[0] = fmaf(sc[j], to_float(vp[1]), o1[0]);
     }
     const float inv = 1.f / den;
-    out[(long long)b * C + h * 64 + lane * 2] = from_float<T>(o0 * inv);
-    out[(long long)b * C + h * 64 + lane * 2 + 1] = from_float<T>(o1 * inv);
+    out[(long long)b * C + h * 64 + lane * 2] = from_float<T>(((o0[0] + o0[1]) + (o0[2] + o0[3])) * inv);
+    out[(long long)b * C + h * 64 + lane * 2 + 1] = from_float<T>(((o1[0] + o1[1]) + (o1[2] + o1[3])) * inv);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -258,12 +313,16 @@ extern "C" int distb200_layernorm(const float* in1, int64_t ld_in1, const float*
     if (!in2) in2_period = 1;
     DISTB200_REQUIRE(in2_period >= 1, "layernorm: in2_period must be >= 1");
     const int wpb = 8;
-    const unsigned grid = (unsigned)((rows + wpb - 1) / wpb);
     cudaStream_t st = (cudaStream_t)stream;
-    if (out_dtype == DISTB200_F32)
-        layernorm_kernel<float><<<grid, wpb * 32, 0, st>>>(in1, ld_in1, in2, ld_in2, in2_period, rows, cols, eps, g1, b1, (float*)y1, ld_y1, g2, b2, (float*)y2, ld_y2);
-    else
-        layernorm_kernel<bf16><<<grid, wpb * 32, 0, st>>>(in1, ld_in1, in2, ld_in2, in2_period, rows, cols, eps, g1, b1, (bf16*)y1, ld_y1, g2, b2, (bf16*)y2, ld_y2);
+#define DISTB200_LN(T, LPR)                                                                                                         \
+    layernorm_kernel<T, LPR><<<(unsigned)((rows + wpb * (32 / LPR) - 1) / (wpb * (32 / LPR))), wpb * 32, 0, st>>>(                  \
+        in1, ld_in1, in2, ld_in2, in2_period, rows, cols, eps, g1, b1, (T*)y1, ld_y1, g2, b2, (T*)y2, ld_y2)
+    if (cols <= 128) {
+        if (out_dtype == DISTB200_F32) DISTB200_LN(float, 8); else DISTB200_LN(bf16, 8);
+    } else {
+        if (out_dtype == DISTB200_F32) DISTB200_LN(float, 32); else DISTB200_LN(bf16, 32);
+    }
+#undef DISTB200_LN
     return check_launch("layernorm");
 }
 
@@ -276,13 +335,20 @@ extern "C" int distb200_patchify(const float* video, void* out, int32_t clips, i
     if (total == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     const long long rows = (long long)clips * n_sel * (H / p) * (W / p);
+    const long long img_rows = (long long)clips * n_sel * 3 * H;
+    const bool v4 = p % 4 == 0 && W % 4 == 0 && ld_out % 4 == 0;
+#define DISTB200_PATCHIFY(T, VEC, TPR)                                                                                             \
+    patchify_kernel<T, VEC, TPR><<<grid_for(img_rows * TPR, 256), 256, 0, st>>>(video, (T*)out, clips, T_, H, W, p, first_frame,   \
+                                                                                 frame_step, n_sel, ld_out)
+    const int T_ = T;
     if (out_dtype == DISTB200_F32) {
-        patchify_kernel<float><<<grid_for(total, 256), 256, 0, st>>>(video, (float*)out, clips, T, H, W, p, first_frame, frame_step, n_sel, ld_out);
+        if (v4) DISTB200_PATCHIFY(float, 4, 64); else DISTB200_PATCHIFY(float, 2, 128);
         if (ld_out > 3 * p * p) zero_pad_cols_kernel<float><<<grid_for(rows * (ld_out - 3 * p * p), 256), 256, 0, st>>>((float*)out, rows, 3 * p * p, ld_out);
     } else {
-        patchify_kernel<bf16><<<grid_for(total, 256), 256, 0, st>>>(video, (bf16*)out, clips, T, H, W, p, first_frame, frame_step, n_sel, ld_out);
+        if (v4) DISTB200_PATCHIFY(bf16, 4, 64); else DISTB200_PATCHIFY(bf16, 2, 128);
         if (ld_out > 3 * p * p) zero_pad_cols_kernel<bf16><<<grid_for(rows * (ld_out - 3 * p * p), 256), 256, 0, st>>>((bf16*)out, rows, 3 * p * p, ld_out);
     }
+#undef DISTB200_PATCHIFY
     return check_launch("patchify");
 }
 

@@ -89,10 +89,12 @@ class PackedWeights:
                 ln=(f32(sd[it + "ln.weight"]), f32(sd[it + "ln.bias"])),
                 ln_t=(f32(sd[it + "ln_temporal.weight"]), f32(sd[it + "ln_temporal.bias"])),
                 fc_w=op(sd[it + "ffn.c_fc.weight"]), fc_b=f32(sd[it + "ffn.c_fc.bias"]),
-                pr_w=op(sd[it + "ffn.c_proj.weight"]), pr_b=f32(sd[it + "ffn.c_proj.bias"]),
+                # ffn.c_proj and temporal_ffn.c_proj are applied as ONE GEMM over the K-concatenated hidden activations
+                # [ffn hidden | temporal hidden]: res = [h_f | h_t] . [W_proj | W_tproj]^T + (b_proj + b_tproj)   (dist.py:45)
+                prj_w=op(torch.cat([sd[it + "ffn.c_proj.weight"].float(), sd[it + "temporal_ffn.c_proj.weight"].float()[:, :, 0, 0, 0]], dim=1)),
+                prj_b=f32(sd[it + "ffn.c_proj.bias"].float() + sd[it + "temporal_ffn.c_proj.bias"].float()),
                 tf1_w=op(sd[it + "temporal_ffn.c_fc1.weight"].float()[:, :, 0, 0, 0]), tf1_b=f32(sd[it + "temporal_ffn.c_fc1.bias"]),
                 tf2_w=op(wk), tf2_b=f32(sd[it + "temporal_ffn.c_fc2.bias"]),
-                tf3_w=op(sd[it + "temporal_ffn.c_proj.weight"].float()[:, :, 0, 0, 0]), tf3_b=f32(sd[it + "temporal_ffn.c_proj.bias"]),
             ))
         self.ada = []
         for j in range(a.ada_layers):
@@ -156,7 +158,7 @@ class DistEngine:
         z = lambda *s, dtype=adt: torch.zeros(*s, device=dev, dtype=dtype)
         f32 = torch.float32
         self.video = z(b, 3, T, a.resolution, a.resolution, dtype=f32)
-        self.patches_s = z(F * P, self.w.kp)
+        self.patches_s = z(F * P, self.w.kp) if a.patch != a.s_patch else None
         self.patches_d = z(b * T * P, self.w.kps)
         self.h = z(Mv, D, dtype=f32)
         self.ln_buf = z(Mv, D)
@@ -173,9 +175,8 @@ class DistEngine:
         self.res = z(Mv, Ci, dtype=f32)
         self.int_a1 = z(Mv, Ci)
         self.int_a2 = z(Mv, Ci)
-        self.ffn_h = z(Mv, a.integration_hidden)
+        self.int_h = z(Mv, a.integration_hidden + a.integration_temporal_hidden)     # [ffn hidden | temporal hidden]
         self.tf1 = z(Mv, a.integration_temporal_hidden)
-        self.tf2 = z(Mv, a.integration_temporal_hidden)
         self.kv_s = z(Mv, 2 * Ci)
         self.sp = z(F, Ci, dtype=f32)
         self.top = z(b, Ci, dtype=f32)
@@ -195,10 +196,10 @@ class DistEngine:
         kw.setdefault("impl", self.gemm_impl)
         self.calls.append(ops.gemm(*args, **kw))
 
-    def _lin(self, a, w, bias, out, *, res=None, out2=None, act=ops.ACT_NONE, name="linear"):
-        """out[M, n] = act(a[M, k] @ w[n, k]^T + bias (+ res))"""
+    def _lin(self, a, w, bias, out, *, res=None, out2=None, act=ops.ACT_NONE, ld_out=None, name="linear"):
+        """out[M, n] = act(a[M, k] @ w[n, k]^T + bias (+ res)); ``ld_out`` > n writes into a column slice of a wider buffer"""
         n, k = w.shape
-        self._gemm(a, w, n, k, bias=bias, res=res, ld_res=n, out=out, ld_out=n, out2=out2, ld_out2=n, act=act, name=name)
+        self._gemm(a, w, n, k, bias=bias, res=res, ld_res=n, out=out, ld_out=ld_out or n, out2=out2, ld_out2=n, act=act, name=name)
 
     def _ln(self, x, gb, y, **kw):
         self.calls.append(ops.layernorm(x, gb[0], gb[1], y, **kw))
@@ -214,12 +215,15 @@ class DistEngine:
 
         # ---- patch rows: sparse frames for the ViT (clip.py:271 restricted to the frames kept at :281-284),
         #      all frames for the temporal stem (dist.py:225)
-        add(ops.patchify(self.video, self.patches_s, b, T, R, R, a.patch, 0, al, t, w.kp, name="patchify.sparse"))
         add(ops.patchify(self.video, self.patches_d, b, T, R, R, a.s_patch, 0, 1, T, w.kps, name="patchify.dense"))
+        shared = a.patch == a.s_patch          # then the ViT's patches are the rows of every alpha-th dense frame
+        if not shared:
+            add(ops.patchify(self.video, self.patches_s, b, T, R, R, a.patch, 0, al, t, w.kp, name="patchify.sparse"))
 
         # ---- ViT embedding: conv1 as GEMM, + positional embedding, class row, ln_pre (clip.py:271-276)
         k1 = 3 * a.patch * a.patch
-        self._gemm(self.patches_s, w.conv1_w, D, k1, a_dim=(k1, P, F, 1), a_stride=(1, w.kp, P * w.kp, F * P * w.kp),
+        src, fstride = (self.patches_d, al * P * w.kp) if shared else (self.patches_s, P * w.kp)
+        self._gemm(src, w.conv1_w, D, k1, a_dim=(k1, P, F, 1), a_stride=(1, w.kp, fstride, F * fstride),
                    groups=F, rows_per_group=P, ldb=w.kp, res=w.pos, ld_res=D, res_gstride=0, res_roff=1,
                    out=self.h, ld_out=D, out_gstride=N, out_roff=1, name="vit.patch_embed")
         add(ops.rows_bcast(self.h, N * D, F, D, w.cls_row, 1, False, name="vit.cls_rows"))   # class embedding + pos[0]
@@ -293,14 +297,15 @@ class DistEngine:
         # ---- IntegrationNetwork (dist.py:16-45) on upd = mid ----
         add(ops.layernorm(self.mid, d["ln"][0], d["ln"][1], self.int_a1, g2=d["ln_t"][0], b2=d["ln_t"][1], y2=self.int_a2,
                           name="dist.int.ln"))
-        self._lin(self.int_a1, d["fc_w"], d["fc_b"], self.ffn_h, act=ops.ACT_QUICKGELU, name="dist.int.ffn_fc")
-        self._lin(self.ffn_h, d["pr_w"], d["pr_b"], self.res, name="dist.int.ffn_proj")
+        Ih = a.integration_hidden
+        wide = Ih + Cm
+        self._lin(self.int_a1, d["fc_w"], d["fc_b"], self.int_h, act=ops.ACT_QUICKGELU, ld_out=wide, name="dist.int.ffn_fc")
         self._lin(self.int_a2, d["tf1_w"], d["tf1_b"], self.tf1, name="dist.int.t_fc1")
         self._gemm(self.tf1, d["tf2_w"], Cm, Cm, a_dim=(Cm, t * N, b, 1), a_stride=(1, Cm, t * N * Cm, Mv * Cm),
                    taps=[((k - half) * N, 0, 0) for k in range(a.t_kernel)], b_tap_stride=Cm * Cm, ldb=Cm,
-                   groups=b, rows_per_group=t * N, bias=d["tf2_b"], out=self.tf2, ld_out=Cm, act=ops.ACT_QUICKGELU,
+                   groups=b, rows_per_group=t * N, bias=d["tf2_b"], out=self.int_h[:, Ih:], ld_out=wide, act=ops.ACT_QUICKGELU,
                    name="dist.int.t_conv")
-        self._lin(self.tf2, d["tf3_w"], d["tf3_b"], self.res, res=self.res, name="dist.int.t_proj")
+        self._lin(self.int_h, d["prj_w"], d["prj_b"], self.res, name="dist.int.proj")
 
     def _plan_head(self):
         a, b, w = self.arch, self.batch, self.w
