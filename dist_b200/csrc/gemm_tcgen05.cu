@@ -47,11 +47,21 @@ struct alignas(64) TcArgs {
     int tiles_per_group;
     int n_tiles;
     int group_dim;
+    int dbg;
     int ctas;                 // 1, or 2 = CTA pair (cta_group::2): 256 rows x block_n per pair, each CTA holds half of B
     uint32_t b_stage_bytes;
     uint32_t tx_bytes;
     long long total_tiles;
 };
+
+// Bottleneck probes, compiled in only with -DDISTB200_GEMM_PROBES and driven by the environment variable
+// DISTB200_GEMM_DBG: 1 = no epilogue memory traffic, 2 = no MMA issue, 4 = no A loads, 8 = no B loads,
+// 16 = no TMEM reads in the epilogue, 32 = one k-iteration per tile.
+#ifdef DISTB200_GEMM_PROBES
+#define PROBE(bit) (args.dbg & (bit))
+#else
+#define PROBE(bit) false
+#endif
 
 struct TileCoord {
     long long gi;
@@ -62,12 +72,16 @@ struct TileCoord {
 // tile = index of a unit of work of one CTA (ctas == 1) or of one CTA pair (ctas == 2, tiles_per_group then counts
 // pairs and the CTA of rank r takes the (2 * pair + r)-th row tile of the group, which may lie past the group's end)
 __device__ __forceinline__ TileCoord decode_tile(const TcArgs& a, long long tile, int rank) {
+    // 32-bit arithmetic: the host guarantees total_tiles < 2^31 (64-bit divisions cost hundreds of cycles on the
+    // single-warp producer / issuer paths)
     TileCoord t;
-    const int n_idx = (int)(tile % a.n_tiles);
-    const long long m_idx = tile / a.n_tiles;
-    t.gi = m_idx / a.tiles_per_group;
-    t.r0 = ((int)(m_idx % a.tiles_per_group) * a.ctas + rank) * a.rows_per_tile;
-    t.n0 = n_idx * a.block_n;
+    const uint32_t tl = (uint32_t)tile;
+    const uint32_t m_idx = tl / (uint32_t)a.n_tiles;
+    const uint32_t n_idx = tl - m_idx * (uint32_t)a.n_tiles;
+    const uint32_t gi = m_idx / (uint32_t)a.tiles_per_group;
+    t.gi = gi;
+    t.r0 = (int)((m_idx - gi * (uint32_t)a.tiles_per_group) * (uint32_t)a.ctas + (uint32_t)rank) * a.rows_per_tile;
+    t.n0 = (int)n_idx * a.block_n;
     return t;
 }
 
@@ -98,27 +112,27 @@ __device__ __forceinline__ void stage_block(const uint32_t* acc, float* stage, i
 //   ACT:  0 none, 1 QuickGELU via tanh.approx.f16x2, 2 QuickGELU via ex2 + rcp
 template <int OUT, bool RES, int ACT>
 struct Epi {
-    // Column domain: lanes 0-15 own the even rows, lanes 16-31 the odd rows of a 32 x 32 block; each lane owns two
-    // adjacent columns.  One loop iteration = two rows: 256 B of fp32 (or 128 B of bf16) per warp instruction.
-    static __device__ __forceinline__ void prefetch(const distb200_gemm_desc& d, float2* rv, long long res_row0, int n, int sub,
+    // Column domain: eight lanes cover the 32 columns of a row (four adjacent columns = 16 bytes each), the four
+    // lane groups take four consecutive rows.  One loop iteration = four rows: 512 B of fp32 (256 B of bf16) per warp
+    // instruction, every row a full 128-byte line.
+    static __device__ __forceinline__ void prefetch(const distb200_gemm_desc& d, float4* rv, float4& bias, long long res_row0, int n, int sub,
                                                     int rows_here, bool col_ok) {
+        bias = (d.bias && col_ok) ? __ldg(reinterpret_cast<const float4*>(d.bias + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
         if (RES) {
             const float* rp = d.res + (res_row0 + sub) * d.ld_res + n;
-            const long long step = 2 * d.ld_res;
+            const long long step = 4 * d.ld_res;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                rv[i] = (col_ok && 2 * i + sub < rows_here) ? *reinterpret_cast<const float2*>(rp) : make_float2(0.f, 0.f);
+            for (int i = 0; i < 8; ++i) {
+                rv[i] = (col_ok && 4 * i + sub < rows_here) ? *reinterpret_cast<const float4*>(rp) : make_float4(0.f, 0.f, 0.f, 0.f);
                 rp += step;
             }
         }
     }
 
-    static __device__ __forceinline__ void finish(const distb200_gemm_desc& d, const float* stage, const float2* rv, int lane, int n,
-                                                  int rows_here, long long dst_row0) {
-        const int sub = lane >> 4, cl = (lane & 15) * 2;
-        float2 bias = make_float2(0.f, 0.f);
-        if (d.bias) bias = __ldg(reinterpret_cast<const float2*>(d.bias + n));
-        const int chunk = cl >> 2, within = cl & 3;
+    template <bool FULL>
+    static __device__ __forceinline__ void finish_rows(const distb200_gemm_desc& d, const float* stage, const float4* rv, const float4 bias,
+                                                       int lane, int n, int rows_here, long long dst_row0) {
+        const int sub = lane >> 3, chunk = lane & 7;
         char* o1 = nullptr;
         char* o2 = nullptr;
         long long s1 = 0, s2 = 0;
@@ -126,45 +140,84 @@ struct Epi {
         if (OUT != 3 || d.out) {
             const int es = f32_1 ? 4 : 2;
             o1 = reinterpret_cast<char*>(d.out) + ((dst_row0 + sub) * d.ld_out + n) * es;
-            s1 = 2 * d.ld_out * es;
+            s1 = 4 * d.ld_out * es;
         }
         const bool f32_2 = OUT == 3 && d.out2_dtype == DISTB200_F32;
         if (OUT == 2 || (OUT == 3 && d.out2)) {
             const int es = f32_2 ? 4 : 2;
             o2 = reinterpret_cast<char*>(d.out2) + ((dst_row0 + sub) * d.ld_out2 + n) * es;
-            s2 = 2 * d.ld_out2 * es;
+            s2 = 4 * d.ld_out2 * es;
+        }
+        const float4* st4 = reinterpret_cast<const float4*>(stage);
+        float4 vv[8];                      // all shared-memory reads first: their latency overlaps instead of serialising
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int row = 4 * i + sub;
+            vv[i] = st4[row * 8 + (chunk ^ (row & 7))];
         }
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            const int row = 2 * i + sub;
-            float2 v = *reinterpret_cast<const float2*>(stage + row * 32 + ((chunk ^ (row & 7)) << 2) + within);
-            v.x += bias.x;
-            v.y += bias.y;
+        for (int i = 0; i < 8; ++i) {
+            const int row = 4 * i + sub;
+            float4 v = vv[i];
+            v.x += bias.x; v.y += bias.y; v.z += bias.z; v.w += bias.w;
             if (RES) {
-                v.x += rv[i].x;
-                v.y += rv[i].y;
+                v.x += rv[i].x; v.y += rv[i].y; v.z += rv[i].z; v.w += rv[i].w;
             }
-            if (ACT == 1) quick_gelu_pair_fast(v.x, v.y);
+            if (ACT == 1) {
+                quick_gelu_pair_fast(v.x, v.y);
+                quick_gelu_pair_fast(v.z, v.w);
+            }
             if (ACT == 2) {
-                v.x = quick_gelu_precise(v.x);
-                v.y = quick_gelu_precise(v.y);
+                v.x = quick_gelu_precise(v.x); v.y = quick_gelu_precise(v.y);
+                v.z = quick_gelu_precise(v.z); v.w = quick_gelu_precise(v.w);
             }
-            if (row < rows_here) {
+            if (FULL || row < rows_here) {
                 if (o1) {
-                    if (f32_1) *reinterpret_cast<float2*>(o1) = v;
-                    else *reinterpret_cast<uint32_t*>(o1) = pack_bf16x2(v.x, v.y);
+                    if (f32_1) *reinterpret_cast<float4*>(o1) = v;
+                    else *reinterpret_cast<uint2*>(o1) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
                 }
                 if (o2) {
-                    if (f32_2) *reinterpret_cast<float2*>(o2) = v;
-                    else *reinterpret_cast<uint32_t*>(o2) = pack_bf16x2(v.x, v.y);
+                    if (f32_2) *reinterpret_cast<float4*>(o2) = v;
+                    else *reinterpret_cast<uint2*>(o2) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
                 }
             }
             o1 += s1;
             o2 += s2;
         }
     }
+
+    static __device__ __forceinline__ void finish(const distb200_gemm_desc& d, const float* stage, const float4* rv, const float4 bias,
+                                                  int lane, int n, int rows_here, long long dst_row0) {
+        if (rows_here >= 32) finish_rows<true>(d, stage, rv, bias, lane, n, rows_here, dst_row0);
+        else finish_rows<false>(d, stage, rv, bias, lane, n, rows_here, dst_row0);
+    }
 };
 
+// Per-tile quantities of one epilogue warp.
+struct EpiTile {
+    long long dst0, res0;
+    int n0, ncols, rows_valid;
+};
+
+__device__ __forceinline__ EpiTile epi_tile(const TcArgs& args, long long tile, int rank, int quad) {
+    const distb200_gemm_desc& d = args.d;
+    const TileCoord tc = decode_tile(args, tile, rank);
+    EpiTile t;
+    const long long rows_left = d.rows_per_group - tc.r0;
+    int rows_valid = (int)(rows_left < args.rows_per_tile ? rows_left : (long long)args.rows_per_tile) - quad * 32;
+    t.rows_valid = rows_valid > 32 ? 32 : rows_valid;                   // rows of this quadrant that exist
+    const long long r = (long long)tc.r0 + quad * 32;
+    t.dst0 = tc.gi * d.out_gstride + d.out_roff + r;
+    t.res0 = tc.gi * d.res_gstride + d.res_roff + r;
+    t.n0 = tc.n0;
+    t.ncols = min(args.block_n, d.n - tc.n0);
+    return t;
+}
+
+// The chunks of a warp form one sequence across its tiles (tile, c0 = half*32, half*32+64, ...).  The residual of
+// chunk i+1 is requested before chunk i is processed, so that a warp always has one chunk of loads (4 KB) in
+// flight while it transposes, activates and stores another: the epilogue of the narrow, short-K GEMMs is bound by
+// the latency of these loads, not by their bandwidth.
 template <int OUT, bool RES, int ACT>
 __device__ __forceinline__ void epilogue_role(const TcArgs& args, uint32_t tmem_base, float* stage, uint32_t tfull0, uint32_t tempty0,
                                               int warp, int lane, long long tile0, long long tile_step, int rank) {
@@ -172,59 +225,80 @@ __device__ __forceinline__ void epilogue_role(const TcArgs& args, uint32_t tmem_
     const distb200_gemm_desc& d = args.d;
     const int quad = warp & 3;              // TMEM lanes [32*quad, 32*quad+32) are the ones this warp may read
     const int half = (warp - 2) >> 2;       // which of the alternating 32-column chunks
-    const int sub = lane >> 4, cl = (lane & 15) * 2;
+    const int sub = lane >> 3, cl = (lane & 7) * 4;
     int acc_stage = 0;
     uint32_t acc_phase = 0;
-    for (long long tile = tile0; tile < args.total_tiles; tile += tile_step) {
-        const TileCoord tc = decode_tile(args, tile, rank);
-        const long long rows_left = d.rows_per_group - tc.r0;
-        int rows_valid = (int)(rows_left < args.rows_per_tile ? rows_left : (long long)args.rows_per_tile) - quad * 32;
-        rows_valid = rows_valid > 32 ? 32 : rows_valid;                 // rows of this quadrant that exist
-        const long long r = (long long)tc.r0 + quad * 32;
-        const long long dst0 = tc.gi * d.out_gstride + d.out_roff + r;
-        const long long res0 = tc.gi * d.res_gstride + d.res_roff + r;
-        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)acc_stage * ACC_STAGE_COLS;
-        const int ncols = min(args.block_n, d.n - tc.n0);
-        bool waited = false;
-        for (int c0 = half * 32; c0 < ncols; c0 += 64) {
-            const int n = tc.n0 + c0 + cl;
-            const bool col_ok = c0 + cl < ncols;
-            float2 rv[16];
-            E::prefetch(d, rv, res0, n, sub, rows_valid, col_ok);      // in flight while the MMAs of the tile finish
-            if (!waited) {
-                ptx::mbar_wait(tfull0 + 8u * acc_stage, acc_phase);
-                ptx::tc_fence_after();
-                waited = true;
-            }
+    if (tile0 >= args.total_tiles) return;
+    long long tile = tile0;
+    EpiTile cur = epi_tile(args, tile, rank, quad);
+    int c0 = half * 32;
+    float4 rv[8], bias = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!PROBE(1) && c0 < cur.ncols) E::prefetch(d, rv, bias, cur.res0, cur.n0 + c0 + cl, sub, cur.rows_valid, c0 + cl < cur.ncols);
+    bool waited = false;
+    while (true) {
+        // ---- next chunk of this warp (possibly in its next tile): request its residual now
+        long long next_tile = tile;
+        int next_c0 = c0 + 64;
+        EpiTile nxt = cur;
+        if (next_c0 >= cur.ncols) {
+            next_tile = tile + tile_step;
+            next_c0 = half * 32;
+            if (next_tile < args.total_tiles) nxt = epi_tile(args, next_tile, rank, quad);
+        }
+        float4 rv2[8], bias2 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (!PROBE(1) && next_tile < args.total_tiles && next_c0 < nxt.ncols)
+            E::prefetch(d, rv2, bias2, nxt.res0, nxt.n0 + next_c0 + cl, sub, nxt.rows_valid, next_c0 + cl < nxt.ncols);
+
+        // ---- current chunk
+        if (!waited) {                       // first chunk of the tile (or no chunk at all: still observe the phase)
+            ptx::mbar_wait(tfull0 + 8u * acc_stage, acc_phase);
+            ptx::tc_fence_after();
+            waited = true;
+        }
+        if (c0 < cur.ncols) {
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)acc_stage * ACC_STAGE_COLS;
+            const int n = cur.n0 + c0 + cl;
+            const bool col_ok = c0 + cl < cur.ncols;
             uint32_t acc[32];
-            const bool two = c0 + 16 < ncols;
-            ptx::tmem_ld16(taddr + (uint32_t)c0, acc);
-            if (two) ptx::tmem_ld16(taddr + (uint32_t)c0 + 16u, acc + 16);
-            ptx::tmem_ld_wait();
-            if (rows_valid > 0) {
+            const bool two = c0 + 16 < cur.ncols;
+            if (!PROBE(16)) {
+                ptx::tmem_ld16(taddr + (uint32_t)c0, acc);
+                if (two) ptx::tmem_ld16(taddr + (uint32_t)c0 + 16u, acc + 16);
+                ptx::tmem_ld_wait();
+            }
+            if (cur.rows_valid > 0 && !PROBE(1)) {
                 stage_block(acc, stage, lane);
                 __syncwarp();
                 for (int rep = 0; rep < d.out_rep; ++rep) {
-                    if (rep > 0) E::prefetch(d, rv, res0 + (long long)rep * d.res_rep_stride, n, sub, rows_valid, col_ok);
-                    if (col_ok) E::finish(d, stage, rv, lane, n, rows_valid, dst0 + (long long)rep * d.out_rep_stride);
+                    if (rep > 0) E::prefetch(d, rv, bias, cur.res0 + (long long)rep * d.res_rep_stride, n, sub, cur.rows_valid, col_ok);
+                    if (col_ok) E::finish(d, stage, rv, bias, lane, n, cur.rows_valid, cur.dst0 + (long long)rep * d.out_rep_stride);
                 }
                 __syncwarp();
             }
         }
-        if (!waited) {                       // this warp had no chunk in the tile: still observe the barrier phase
-            ptx::mbar_wait(tfull0 + 8u * acc_stage, acc_phase);
-            ptx::tc_fence_after();
+        if (next_tile != tile) {
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                // the accumulator stage is released to the MMA issuer, which lives in the leader CTA of a pair
+                if (rank == 0) ptx::mbar_arrive(tempty0 + 8u * acc_stage);
+                else ptx::mbar_arrive_cluster(ptx::mapa(tempty0 + 8u * acc_stage, 0));
+            }
+            if (++acc_stage == 2) { acc_stage = 0; acc_phase ^= 1u; }
+            waited = false;
+            if (next_tile >= args.total_tiles) break;
         }
-        ptx::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) {
-            // the accumulator stage is released to the MMA issuer, which lives in the leader CTA of a pair
-            if (rank == 0) ptx::mbar_arrive(tempty0 + 8u * acc_stage);
-            else ptx::mbar_arrive_cluster(ptx::mapa(tempty0 + 8u * acc_stage, 0));
+        tile = next_tile;
+        c0 = next_c0;
+        cur = nxt;
+        bias = bias2;
+        if (RES) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) rv[i] = rv2[i];
         }
-        if (++acc_stage == 2) { acc_stage = 0; acc_phase ^= 1u; }
     }
 }
+
 
 template <int CTAS>
 __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __grid_constant__ TcArgs args) {
@@ -272,7 +346,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
 
-    const int iters = d.num_taps * args.k_blocks;
+    const int iters = PROBE(32) ? 1 : d.num_taps * args.k_blocks;
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -284,39 +358,50 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
             const int b_rows = args.block_n / CTAS;     // a pair splits the B tile: rank r holds rows [r * block_n / 2, ...)
             for (long long tile = tile0; tile < args.total_tiles; tile += tile_step) {
                 const TileCoord tc = decode_tile(args, tile, rank);
-                for (int it = 0; it < iters; ++it) {
-                    const int tap = it / args.k_blocks;
-                    const int kb = it - tap * args.k_blocks;
-                    ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
-                    const uint32_t sa = smem_base + (uint32_t)stage * stage_bytes;
-                    const uint32_t sb = sa + A_STAGE_BYTES;
+                const int img_row0 = d.img_w > 0 ? tc.r0 / d.img_w : 0;
+                for (int tap = 0; tap < (PROBE(32) ? 1 : d.num_taps); ++tap) {
                     int c1, c2, c3;
                     if (d.img_w > 0) {
                         c1 = d.tap_off[tap][0];
-                        c2 = tc.r0 / d.img_w + d.tap_off[tap][1];
+                        c2 = img_row0 + d.tap_off[tap][1];
                         c3 = (int)tc.gi + d.tap_off[tap][2];
                     } else {
                         c1 = tc.r0 + d.tap_off[tap][0];
                         c2 = d.tap_off[tap][1] + (args.group_dim == 3 ? 0 : (int)tc.gi);
                         c3 = d.tap_off[tap][2] + (args.group_dim == 3 ? (int)tc.gi : 0);
                     }
-                    if (CTAS == 2) {
-                        // All bytes of the pair are counted on the leader's barrier, where the MMA issuer waits.  The peer
-                        // needs no arrive of its own: it can only refill a stage after the leader's MMAs released it
-                        // (multicast commit below), i.e. after the barrier's previous phase completed.
-                        const uint32_t lead_full = ptx::mapa(full_bar(stage), 0);
-                        if (ptx::elect_one()) {
-                            if (rank == 0) ptx::mbar_arrive_expect_tx(full_bar(stage), 2 * args.tx_bytes);
-                            ptx::tma_load_4d_2sm(sa, &args.tm_a, lead_full, kb * BLOCK_K, c1, c2, c3);
-                            ptx::tma_load_3d_2sm(sb, &args.tm_b, lead_full, kb * BLOCK_K, tc.n0 + rank * b_rows, tap);
+                    for (int kb = 0; kb < (PROBE(32) ? 1 : args.k_blocks); ++kb) {
+                        ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
+                        const uint32_t sa = smem_base + (uint32_t)stage * stage_bytes;
+                        const uint32_t sb = sa + A_STAGE_BYTES;
+                        if (CTAS == 2) {
+                            // All bytes of the pair are counted on the leader's barrier, where the MMA issuer waits.  The peer
+                            // needs no arrive of its own: it can only refill a stage after the leader's MMAs released it
+                            // (multicast commit below), i.e. after the barrier's previous phase completed.
+                            const uint32_t lead_full = ptx::mapa(full_bar(stage), 0);
+                            if (ptx::elect_one()) {
+                                if (rank == 0) ptx::mbar_arrive_expect_tx(full_bar(stage), 2 * args.tx_bytes);
+                                ptx::tma_load_4d_2sm(sa, &args.tm_a, lead_full, kb * BLOCK_K, c1, c2, c3);
+                                ptx::tma_load_3d_2sm(sb, &args.tm_b, lead_full, kb * BLOCK_K, tc.n0 + rank * b_rows, tap);
+                            }
+                        } else if (ptx::elect_one()) {
+#ifdef DISTB200_GEMM_PROBES
+                            uint32_t tx = args.tx_bytes;
+                            const uint32_t b_bytes = (uint32_t)(BLOCK_K * args.block_n * 2);
+                            if (PROBE(4)) tx -= args.tx_bytes - b_bytes;
+                            if (PROBE(8)) tx -= b_bytes;
+                            if (tx) ptx::mbar_arrive_expect_tx(full_bar(stage), tx); else ptx::mbar_arrive(full_bar(stage));
+                            if (!PROBE(4)) ptx::tma_load_4d(sa, &args.tm_a, full_bar(stage), kb * BLOCK_K, c1, c2, c3);
+                            if (!PROBE(8)) ptx::tma_load_3d(sb, &args.tm_b, full_bar(stage), kb * BLOCK_K, tc.n0, tap);
+#else
+                            ptx::mbar_arrive_expect_tx(full_bar(stage), args.tx_bytes);
+                            ptx::tma_load_4d(sa, &args.tm_a, full_bar(stage), kb * BLOCK_K, c1, c2, c3);
+                            ptx::tma_load_3d(sb, &args.tm_b, full_bar(stage), kb * BLOCK_K, tc.n0, tap);
+#endif
                         }
-                    } else if (ptx::elect_one()) {
-                        ptx::mbar_arrive_expect_tx(full_bar(stage), args.tx_bytes);
-                        ptx::tma_load_4d(sa, &args.tm_a, full_bar(stage), kb * BLOCK_K, c1, c2, c3);
-                        ptx::tma_load_3d(sb, &args.tm_b, full_bar(stage), kb * BLOCK_K, tc.n0, tap);
+                        __syncwarp();
+                        if (++stage == args.stages) { stage = 0; phase ^= 1u; }
                     }
-                    __syncwarp();
-                    if (++stage == args.stages) { stage = 0; phase ^= 1u; }
                 }
             }
         }
@@ -325,6 +410,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
         // Whole warp in the loop, one elected lane issues tcgen05.mma / tcgen05.commit (see the producer).
         if (rank == 0) {
             const uint32_t idesc = ptx::umma_idesc_bf16(BLOCK_M * CTAS, args.block_n);
+            const uint64_t desc0 = ptx::umma_desc_k_sw128(smem_base);          // stage bases are 1024-byte multiples: no carry into other fields
+            const int ksteps_last = (d.k - (args.k_blocks - 1) * BLOCK_K + 15) / 16;
             int stage = 0;
             uint32_t phase = 0;
             int acc_stage = 0;
@@ -333,17 +420,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
                 ptx::mbar_wait(tempty_bar(acc_stage), acc_phase ^ 1u);
                 ptx::tc_fence_after();
                 const uint32_t tmem_d = tmem_base + (uint32_t)acc_stage * ACC_STAGE_COLS;
+                int kb = 0;
                 for (int it = 0; it < iters; ++it) {
-                    const int kb = it % args.k_blocks;
                     ptx::mbar_wait(full_bar(stage), phase);
                     ptx::tc_fence_after();
-                    const uint32_t sa = smem_base + (uint32_t)stage * stage_bytes;
-                    const uint64_t da = ptx::umma_desc_k_sw128(sa);
-                    const uint64_t db = ptx::umma_desc_k_sw128(sa + A_STAGE_BYTES);
-                    int ksteps = (d.k - kb * BLOCK_K + 15) / 16;
-                    ksteps = ksteps > BLOCK_K / 16 ? BLOCK_K / 16 : ksteps;
+                    const uint64_t da = desc0 + (uint64_t)(((uint32_t)stage * stage_bytes) >> 4);
+                    const uint64_t db = da + (uint64_t)(A_STAGE_BYTES >> 4);
+                    const int ksteps = kb == args.k_blocks - 1 ? ksteps_last : BLOCK_K / 16;
                     if (ptx::elect_one()) {
-                        for (int ks = 0; ks < ksteps; ++ks) {
+                        for (int ks = 0; ks < (PROBE(2) ? 0 : ksteps); ++ks) {
                             // advancing 16 bf16 (32 bytes) along K inside the swizzle row: +2 in the (addr >> 4) field
                             if (CTAS == 2) ptx::mma_f16_ss_2sm(tmem_d, da + (uint64_t)(2 * ks), db + (uint64_t)(2 * ks), idesc, (it | ks) != 0);
                             else ptx::mma_f16_ss(tmem_d, da + (uint64_t)(2 * ks), db + (uint64_t)(2 * ks), idesc, (it | ks) != 0);
@@ -353,6 +438,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
                     }
                     __syncwarp();
                     if (++stage == args.stages) { stage = 0; phase ^= 1u; }
+                    if (++kb == args.k_blocks) kb = 0;
                 }
                 if (ptx::elect_one()) {
                     if (CTAS == 2) ptx::mma_commit_2sm(tfull_bar(acc_stage), 3);    // both CTAs' epilogues may start
@@ -496,8 +582,11 @@ int gemm_tcgen05_launch(const distb200_gemm_desc& d, cudaStream_t stream) {
         DISTB200_REQUIRE(args.block_n % 32 == 0, "gemm(tcgen05): CTA pairs need block_n %% 32 == 0 (block_n=%d)", args.block_n);
         args.ctas = 2;
     }
+    static const int dbg_env = getenv("DISTB200_GEMM_DBG") ? atoi(getenv("DISTB200_GEMM_DBG")) : 0;
+    args.dbg = dbg_env;
     args.tiles_per_group = (row_tiles + args.ctas - 1) / args.ctas;
     args.total_tiles = d.groups * args.tiles_per_group * args.n_tiles;
+    DISTB200_REQUIRE(args.total_tiles < (1ll << 31) && d.groups < (1ll << 31), "gemm(tcgen05): too many tiles (%lld)", args.total_tiles);
     args.b_stage_bytes = (uint32_t)(args.block_n / args.ctas) * BLOCK_K * 2;
     const uint32_t stage_bytes = A_STAGE_BYTES + args.b_stage_bytes;
     args.stages = SMEM_BUDGET / (int)stage_bytes;
