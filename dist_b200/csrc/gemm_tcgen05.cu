@@ -28,13 +28,14 @@ namespace {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;             // 64 bf16 = one 128-byte swizzle row
 constexpr int MAX_STAGES = 8;
-constexpr int EPI_WARPS = 8;
-constexpr int NUM_THREADS = 64 + EPI_WARPS * 32;
-constexpr int STAGING_BYTES = EPI_WARPS * 32 * 32 * 4;
+// Epilogue warps: 4 TMEM lane quadrants x EW/4 interleaved 32-column chunks.  8 warps leave room for the deepest
+// operand ring (long-K GEMMs), 12 warps hide more of the epilogue's latency (narrow / short-K GEMMs).
+__host__ __device__ constexpr int num_threads(int ew) { return 64 + ew * 32; }
+__host__ __device__ constexpr int staging_bytes(int ew) { return ew * 32 * 32 * 4; }
+__host__ __device__ constexpr int smem_budget(int ew) { return 227 * 1024 - staging_bytes(ew) - 2048; }
 constexpr uint32_t A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
 constexpr uint32_t TMEM_COLS = 512;
 constexpr uint32_t ACC_STAGE_COLS = 256;
-constexpr int SMEM_BUDGET = 227 * 1024 - STAGING_BYTES - 2048;
 
 struct alignas(64) TcArgs {
     CUtensorMap tm_a;
@@ -218,7 +219,7 @@ __device__ __forceinline__ EpiTile epi_tile(const TcArgs& args, long long tile, 
 // chunk i+1 is requested before chunk i is processed, so that a warp always has one chunk of loads (4 KB) in
 // flight while it transposes, activates and stores another: the epilogue of the narrow, short-K GEMMs is bound by
 // the latency of these loads, not by their bandwidth.
-template <int OUT, bool RES, int ACT>
+template <int OUT, bool RES, int ACT, int EW>
 __device__ __forceinline__ void epilogue_role(const TcArgs& args, uint32_t tmem_base, float* stage, uint32_t tfull0, uint32_t tempty0,
                                               int warp, int lane, long long tile0, long long tile_step, int rank) {
     typedef Epi<OUT, RES, ACT> E;
@@ -232,21 +233,24 @@ __device__ __forceinline__ void epilogue_role(const TcArgs& args, uint32_t tmem_
     long long tile = tile0;
     EpiTile cur = epi_tile(args, tile, rank, quad);
     int c0 = half * 32;
+    constexpr int CSTEP = 32 * (EW / 4);
+    constexpr bool EPI_PIPE_RES = EW <= 8;       // double-buffered residual prefetch only when registers allow
     float4 rv[8], bias = make_float4(0.f, 0.f, 0.f, 0.f);
     if (!PROBE(1) && c0 < cur.ncols) E::prefetch(d, rv, bias, cur.res0, cur.n0 + c0 + cl, sub, cur.rows_valid, c0 + cl < cur.ncols);
     bool waited = false;
     while (true) {
         // ---- next chunk of this warp (possibly in its next tile): request its residual now
         long long next_tile = tile;
-        int next_c0 = c0 + 64;
+        int next_c0 = c0 + CSTEP;
         EpiTile nxt = cur;
         if (next_c0 >= cur.ncols) {
             next_tile = tile + tile_step;
             next_c0 = half * 32;
             if (next_tile < args.total_tiles) nxt = epi_tile(args, next_tile, rank, quad);
         }
-        float4 rv2[8], bias2 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (!PROBE(1) && next_tile < args.total_tiles && next_c0 < nxt.ncols)
+        float4 rv2[EPI_PIPE_RES ? 8 : 1], bias2 = make_float4(0.f, 0.f, 0.f, 0.f);
+        const bool have_next = !PROBE(1) && next_tile < args.total_tiles && next_c0 < nxt.ncols;
+        if (EPI_PIPE_RES && have_next)
             E::prefetch(d, rv2, bias2, nxt.res0, nxt.n0 + next_c0 + cl, sub, nxt.rows_valid, next_c0 + cl < nxt.ncols);
 
         // ---- current chunk
@@ -291,17 +295,21 @@ __device__ __forceinline__ void epilogue_role(const TcArgs& args, uint32_t tmem_
         tile = next_tile;
         c0 = next_c0;
         cur = nxt;
-        bias = bias2;
-        if (RES) {
+        if (EPI_PIPE_RES) {
+            bias = bias2;
+            if (RES) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) rv[i] = rv2[i];
+                for (int i = 0; i < 8; ++i) rv[i] = rv2[i];
+            }
+        } else if (have_next) {
+            E::prefetch(d, rv, bias, cur.res0, cur.n0 + c0 + cl, sub, cur.rows_valid, c0 + cl < cur.ncols);
         }
     }
 }
 
 
-template <int CTAS>
-__global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __grid_constant__ TcArgs args) {
+template <int CTAS, int EW>
+__global__ void __launch_bounds__(num_threads(EW), 1) gemm_tcgen05_kernel(const __grid_constant__ TcArgs args) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const distb200_gemm_desc& d = args.d;
 
@@ -310,7 +318,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
     const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t stage_bytes = A_STAGE_BYTES + args.b_stage_bytes;
     const uint32_t staging_base = smem_base + (uint32_t)args.stages * stage_bytes;
-    const uint32_t bar_base = staging_base + STAGING_BYTES;
+    const uint32_t bar_base = staging_base + staging_bytes(EW);
     // barriers (8 bytes each): full[MAX_STAGES], empty[MAX_STAGES], tmem_full[2], tmem_empty[2], then the TMEM base
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (MAX_STAGES + s); };
@@ -333,7 +341,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
         }
         for (int s = 0; s < 2; ++s) {
             ptx::mbar_init(tfull_bar(s), 1);
-            ptx::mbar_init(tempty_bar(s), EPI_WARPS * CTAS);
+            ptx::mbar_init(tempty_bar(s), EW * CTAS);
         }
         ptx::fence_barrier_init();
     }
@@ -456,7 +464,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
         const bool bf_only = d.out && d.out_dtype == DISTB200_BF16 && !d.out2;
         const bool f_only = d.out && d.out_dtype == DISTB200_F32 && !d.out2;
         const bool f_and_bf = d.out && d.out_dtype == DISTB200_F32 && d.out2 && d.out2_dtype == DISTB200_BF16;
-#define DISTB200_EPI(OUT, RES, ACT) epilogue_role<OUT, RES, ACT>(args, tmem_base, stage, tf, te, warp, lane, tile0, tile_step, rank)
+#define DISTB200_EPI(OUT, RES, ACT) epilogue_role<OUT, RES, ACT, EW>(args, tmem_base, stage, tf, te, warp, lane, tile0, tile_step, rank)
         if (bf_only && !d.res && !gelu) DISTB200_EPI(1, false, 0);
         else if (bf_only && !d.res && gelu) DISTB200_EPI(1, false, 1);
         else if (f_only && d.res && !gelu) DISTB200_EPI(0, true, 0);
@@ -589,7 +597,10 @@ int gemm_tcgen05_launch(const distb200_gemm_desc& d, cudaStream_t stream) {
     DISTB200_REQUIRE(args.total_tiles < (1ll << 31) && d.groups < (1ll << 31), "gemm(tcgen05): too many tiles (%lld)", args.total_tiles);
     args.b_stage_bytes = (uint32_t)(args.block_n / args.ctas) * BLOCK_K * 2;
     const uint32_t stage_bytes = A_STAGE_BYTES + args.b_stage_bytes;
-    args.stages = SMEM_BUDGET / (int)stage_bytes;
+    // epilogue width: long reductions want the deepest operand ring, everything else the better latency hiding
+    static const int ew_env = getenv("DISTB200_GEMM_EPI_WARPS") ? atoi(getenv("DISTB200_GEMM_EPI_WARPS")) : 0;
+    const int ew = ew_env == 8 || ew_env == 12 ? ew_env : ((long long)d.k * d.num_taps >= 2048 ? 8 : 12);
+    args.stages = smem_budget(ew) / (int)stage_bytes;
     if (args.stages > MAX_STAGES) args.stages = MAX_STAGES;
     if (args.stages < 2) args.stages = 2;
 
@@ -616,34 +627,40 @@ int gemm_tcgen05_launch(const distb200_gemm_desc& d, cudaStream_t stream) {
         args.tx_bytes += (uint32_t)(BLOCK_K * (args.block_n / args.ctas) * 2);
     }
 
-    const int smem = args.stages * (int)stage_bytes + STAGING_BYTES + 1024 + 8 * (2 * MAX_STAGES + 4) + 16;
+    const int smem = args.stages * (int)stage_bytes + staging_bytes(ew) + 1024 + 8 * (2 * MAX_STAGES + 4) + 16;
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tcgen05_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        DISTB200_REQUIRE(e == cudaSuccess, "gemm(tcgen05): cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+        const void* fns[4] = {(const void*)gemm_tcgen05_kernel<1, 8>, (const void*)gemm_tcgen05_kernel<2, 8>,
+                              (const void*)gemm_tcgen05_kernel<1, 12>, (const void*)gemm_tcgen05_kernel<2, 12>};
+        for (int i = 0; i < 4; ++i) {
+            cudaError_t e = cudaFuncSetAttribute(fns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+            DISTB200_REQUIRE(e == cudaSuccess, "gemm(tcgen05): cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+        }
         attr_done = true;
     }
+    cudaLaunchConfig_t cfg = {};
+    cfg.blockDim = dim3((unsigned)num_threads(ew));
+    cfg.dynamicSmemBytes = (size_t)smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    cfg.attrs = attr;
+    cudaError_t e;
     if (args.ctas == 2) {
         long long clusters = args.total_tiles < sm_count() / 2 ? args.total_tiles : sm_count() / 2;
-        cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3((unsigned)(2 * clusters));
-        cfg.blockDim = dim3(NUM_THREADS);
-        cfg.dynamicSmemBytes = (size_t)smem;
-        cfg.stream = stream;
-        cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = 2;
         attr[0].val.clusterDim.y = 1;
         attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr;
         cfg.numAttrs = 1;
-        cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<2>, args);
-        DISTB200_REQUIRE(e == cudaSuccess, "gemm(tcgen05): cluster launch failed: %s", cudaGetErrorString(e));
+        e = ew == 8 ? cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<2, 8>, args) : cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<2, 12>, args);
     } else {
         long long grid = args.total_tiles < sm_count() ? args.total_tiles : sm_count();
-        gemm_tcgen05_kernel<1><<<(unsigned)grid, NUM_THREADS, smem, stream>>>(args);
+        cfg.gridDim = dim3((unsigned)grid);
+        cfg.numAttrs = 0;
+        e = ew == 8 ? cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<1, 8>, args) : cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<1, 12>, args);
     }
+    DISTB200_REQUIRE(e == cudaSuccess, "gemm(tcgen05): launch failed: %s", cudaGetErrorString(e));
     return check_launch("gemm_tcgen05");
 }
 
