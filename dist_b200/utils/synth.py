@@ -202,6 +202,24 @@ def synth_text_features(num_classes, embed_dim, seed=77):
     return torch.randn(num_classes, embed_dim, generator=g, dtype=torch.float32)
 
 
+def synth_soft_targets(batch, num_classes, seed=99, smoothing=0.1):
+    """Soft labels ``[b, C]`` of the kind mixup / cutmix + label smoothing produce (``dataset/utils/mixup.py:103-319``):
+    each row mixes two smoothed one-hot labels with a Beta(0.8, 0.8)-like weight and sums to one."""
+    g = torch.Generator(device="cpu")
+    g.manual_seed(int(seed))
+    a = torch.randint(0, num_classes, (batch,), generator=g)
+    b = torch.randint(0, num_classes, (batch,), generator=g)
+    lam = torch.rand(batch, generator=g, dtype=torch.float32).clamp(0.05, 0.95)
+    off, on = smoothing / num_classes, 1.0 - smoothing + smoothing / num_classes
+
+    def one_hot(idx):
+        t = torch.full((batch, num_classes), off, dtype=torch.float32)
+        t.scatter_(1, idx.view(-1, 1), on)
+        return t
+
+    return lam.view(-1, 1) * one_hot(a) + (1.0 - lam.view(-1, 1)) * one_hot(b)
+
+
 def checksum(tensors):
     """Order-independent fingerprint of a tensor or dict of tensors (float64 sums)."""
     if isinstance(tensors, torch.Tensor):
