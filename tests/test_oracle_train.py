@@ -78,7 +78,7 @@ def test_train_step_reduces_loss():
     cur = dict(sd)
     losses = []
     for _ in range(3):
-        loss, cur = train_oracle.train_step(cur, state, clips, text, target, arch, lr=3e-3, weight_decay=1e-4)
+        loss, cur = train_oracle.train_step(cur, state, clips, text, target, arch, lr=2e-4, weight_decay=1e-4)
         losses.append(float(loss))
     assert losses[2] < losses[0]
     for k in train_oracle.unused_names(arch):
