@@ -54,6 +54,23 @@ extern "C" int distb200_gemm(const distb200_gemm_desc* desc, void* stream) {
     return gemm_tcgen05_launch(d, st);
 }
 
+extern "C" int distb200_gemm_wgrad(const distb200_wgrad_desc* desc, void* stream) {
+    DISTB200_REQUIRE(desc != nullptr, "gemm_wgrad: null descriptor");
+    const distb200_wgrad_desc& d = *desc;
+    DISTB200_REQUIRE(d.x && d.dy && d.dw, "gemm_wgrad: null pointer");
+    DISTB200_REQUIRE(d.dtype == DISTB200_F32 || d.dtype == DISTB200_BF16, "gemm_wgrad: unknown dtype %d", d.dtype);
+    DISTB200_REQUIRE(d.num_taps >= 1 && d.num_taps <= DISTB200_MAX_TAPS, "gemm_wgrad: num_taps=%d out of range", d.num_taps);
+    DISTB200_REQUIRE(d.groups >= 0 && d.rows_per_group >= 0 && d.n >= 1 && d.k >= 1, "gemm_wgrad: bad sizes");
+    DISTB200_REQUIRE(d.group_dim == 0 || d.group_dim == 2 || d.group_dim == 3, "gemm_wgrad: group_dim must be 2 or 3");
+    DISTB200_REQUIRE(d.ld_dw >= d.k, "gemm_wgrad: ld_dw too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (d.impl == DISTB200_IMPL_SIMT || d.dtype == DISTB200_F32) {
+        DISTB200_REQUIRE(d.impl == DISTB200_IMPL_AUTO || d.impl == DISTB200_IMPL_SIMT, "gemm_wgrad: the tcgen05 kernel needs bf16 operands");
+        return wgrad_simt_launch(d, st);
+    }
+    return wgrad_tcgen05_launch(d, st);
+}
+
 extern "C" int distb200_attention(const void* qkv, void* out, int32_t frames, int32_t tokens, int32_t heads, int32_t dtype,
                                   int32_t impl, void* stream) {
     if (frames == 0) return 0;

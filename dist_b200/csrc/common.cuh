@@ -71,5 +71,7 @@ inline int sm_count() {
 // implemented in gemm_tcgen05.cu / gemm_simt.cu
 int gemm_tcgen05_launch(const distb200_gemm_desc& d, cudaStream_t stream);
 int gemm_simt_launch(const distb200_gemm_desc& d, cudaStream_t stream);
+int wgrad_simt_launch(const distb200_wgrad_desc& d, cudaStream_t stream);
+int wgrad_tcgen05_launch(const distb200_wgrad_desc& d, cudaStream_t stream);
 
 }  // namespace distb200

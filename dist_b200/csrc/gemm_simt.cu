@@ -112,6 +112,69 @@ __global__ void __launch_bounds__(NT) gemm_simt_kernel(const SimtArgs args) {
     }
 }
 
+
+// ---- weight gradient (distb200_gemm_wgrad), FFMA version: the fp32 parity path and the cross-check of the tensor-core
+// kernel.  Block = 16 (n) x 16 (k) outputs of one tap; the rows are split over blockIdx.z and reduced with fp32 atomics.
+constexpr int WT = 16, WR = 32;
+
+struct WgradSimtArgs {
+    distb200_wgrad_desc d;
+    long long total_rows;
+    long long rows_per_split;
+    int splits;
+    int n_tiles;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(WT * WT) wgrad_simt_kernel(const WgradSimtArgs args) {
+    const distb200_wgrad_desc& d = args.d;
+    __shared__ float Ys[WR][WT + 1];
+    __shared__ float Xs[WR][WT + 1];
+    const int tid = threadIdx.x, tn = tid / WT, tk = tid % WT;
+    const int n0 = (blockIdx.x % args.n_tiles) * WT, tap = blockIdx.x / args.n_tiles;
+    const int k0 = blockIdx.y * WT;
+    const int split = blockIdx.z;
+    const T* __restrict__ X = reinterpret_cast<const T*>(d.x);
+    const T* __restrict__ DY = reinterpret_cast<const T*>(d.dy);
+    const long long r_begin = (long long)split * args.rows_per_split;
+    long long r_end = r_begin + args.rows_per_split;
+    if (r_end > args.total_rows) r_end = args.total_rows;
+    const int ka = (int)(d.a_dim[0] < d.k ? d.a_dim[0] : d.k);
+    float acc = 0.f;
+    for (long long base = r_begin; base < r_end; base += WR) {
+        // loader: thread (lr, lc) fetches rows lr and lr + 16 of the chunk, column lc of each operand tile
+        for (int h = 0; h < WR / WT; ++h) {
+            const int lr = tn + h * WT, lc = tk;
+            const long long row = base + lr;
+            float yv = 0.f, xv = 0.f;
+            if (row < r_end) {
+                const long long gi = row / d.rows_per_group, r = row - gi * d.rows_per_group;
+                if (n0 + lc < d.n) yv = to_float(DY[(gi * d.dy_gstride + d.dy_roff + r) * d.ld_dy + n0 + lc]);
+                long long c1, c2, c3;
+                if (d.img_w > 0) {
+                    c1 = r % d.img_w + d.tap_off[tap][0];
+                    c2 = r / d.img_w + d.tap_off[tap][1];
+                    c3 = gi + d.tap_off[tap][2];
+                } else {
+                    c1 = r + d.tap_off[tap][0];
+                    c2 = d.tap_off[tap][1] + (d.group_dim == 3 ? 0 : gi);
+                    c3 = d.tap_off[tap][2] + (d.group_dim == 3 ? gi : 0);
+                }
+                const bool ok = c1 >= 0 && c1 < d.a_dim[1] && c2 >= 0 && c2 < d.a_dim[2] && c3 >= 0 && c3 < d.a_dim[3] && k0 + lc < ka;
+                if (ok) xv = to_float(X[c1 * d.a_stride[1] + c2 * d.a_stride[2] + c3 * d.a_stride[3] + k0 + lc]);
+            }
+            Ys[lr][lc] = yv;
+            Xs[lr][lc] = xv;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < WR; ++r) acc = fmaf(Ys[r][tn], Xs[r][tk], acc);
+        __syncthreads();
+    }
+    if (n0 + tn < d.n && k0 + tk < d.k)
+        atomicAdd(d.dw + (long long)tap * d.dw_tap_stride + (long long)(n0 + tn) * d.ld_dw + k0 + tk, acc);
+}
+
 }  // namespace
 
 int gemm_simt_launch(const distb200_gemm_desc& d, cudaStream_t stream) {
@@ -125,6 +188,27 @@ int gemm_simt_launch(const distb200_gemm_desc& d, cudaStream_t stream) {
     if (d.dtype == DISTB200_F32) gemm_simt_kernel<float><<<grid, NT, 0, stream>>>(args);
     else gemm_simt_kernel<bf16><<<grid, NT, 0, stream>>>(args);
     return check_launch("gemm_simt");
+}
+
+int wgrad_simt_launch(const distb200_wgrad_desc& d, cudaStream_t stream) {
+    WgradSimtArgs args;
+    args.d = d;
+    args.total_rows = (long long)d.groups * d.rows_per_group;
+    if (args.total_rows == 0 || d.n == 0 || d.k == 0) return 0;
+    args.n_tiles = (d.n + WT - 1) / WT;
+    const int k_tiles = (d.k + WT - 1) / WT;
+    const long long blocks_xy = (long long)args.n_tiles * d.num_taps * k_tiles;
+    long long splits = ((long long)sm_count() * 8 + blocks_xy - 1) / blocks_xy;
+    const long long max_splits = (args.total_rows + 4 * WR - 1) / (4 * WR);
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+    if (splits > 65535) splits = 65535;
+    args.rows_per_split = ((args.total_rows + splits - 1) / splits + WR - 1) / WR * WR;
+    args.splits = (int)((args.total_rows + args.rows_per_split - 1) / args.rows_per_split);
+    dim3 grid((unsigned)(args.n_tiles * d.num_taps), (unsigned)k_tiles, (unsigned)args.splits);
+    if (d.dtype == DISTB200_F32) wgrad_simt_kernel<float><<<grid, WT * WT, 0, stream>>>(args);
+    else wgrad_simt_kernel<bf16><<<grid, WT * WT, 0, stream>>>(args);
+    return check_launch("wgrad_simt");
 }
 
 }  // namespace distb200

@@ -1,0 +1,584 @@
+// Backward-pass and optimizer kernels of the fine-tuning step other than the GEMMs:
+// QuickGELU forward / backward on saved pre-activations, casts, frame-group sums, column sums (bias-like gradients),
+// LayerNorm backward, single-query cross-attention backward, the soft-target cross-entropy head, AdamW and the
+// operand copies of the master weights.  All HBM-bound: vectorised accesses, warp-shuffle reductions, fp32 math.
+#include "common.cuh"
+
+namespace distb200 {
+
+namespace {
+
+inline unsigned grid_cap(long long work, int block, int per_sm = 16) {
+    long long g = (work + block - 1) / block;
+    const long long cap = (long long)sm_count() * per_sm;
+    return (unsigned)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+__device__ __forceinline__ float ld_any(const void* p, int dtype, long long i) {
+    return dtype == DISTB200_F32 ? reinterpret_cast<const float*>(p)[i] : __bfloat162float(reinterpret_cast<const bf16*>(p)[i]);
+}
+__device__ __forceinline__ void st_any(void* p, int dtype, long long i, float v) {
+    if (dtype == DISTB200_F32) reinterpret_cast<float*>(p)[i] = v;
+    else reinterpret_cast<bf16*>(p)[i] = __float2bfloat16_rn(v);
+}
+
+// four consecutive elements (i % 4 == 0, 16 / 8-byte aligned)
+__device__ __forceinline__ float4 ld4_any(const void* p, int dtype, long long i) {
+    if (dtype == DISTB200_F32) return *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p) + i);
+    const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const bf16*>(p) + i);
+    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+    const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ void st4_any(void* p, int dtype, long long i, float4 v) {
+    if (dtype == DISTB200_F32) *reinterpret_cast<float4*>(reinterpret_cast<float*>(p) + i) = v;
+    else *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p) + i) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+}
+
+__device__ __forceinline__ float qgelu_grad(float z) {
+    const float s = 1.0f / (1.0f + __expf(-1.702f * z));
+    return s * (1.0f + 1.702f * z * (1.0f - s));
+}
+
+// ---------------------------------------------------------------------------------------------------
+// elementwise (n % 4 == 0 fast path, scalar tail)
+// ---------------------------------------------------------------------------------------------------
+enum { EW_GELU = 0, EW_GELU_BWD = 1, EW_CAST = 2 };
+
+template <int OP>
+__global__ void __launch_bounds__(256) elementwise_kernel(const void* a, int a_dtype, const void* b, int b_dtype, float* o32, void* olp,
+                                                          int lp_dtype, long long n) {
+    const long long n4 = n >> 2;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const float4 x = ld4_any(a, a_dtype, 4 * i);
+        float4 r;
+        if (OP == EW_GELU) {
+            r = make_float4(quick_gelu(x.x), quick_gelu(x.y), quick_gelu(x.z), quick_gelu(x.w));
+        } else if (OP == EW_GELU_BWD) {
+            const float4 z = ld4_any(b, b_dtype, 4 * i);
+            r = make_float4(x.x * qgelu_grad(z.x), x.y * qgelu_grad(z.y), x.z * qgelu_grad(z.z), x.w * qgelu_grad(z.w));
+        } else {
+            r = x;
+        }
+        if (o32) *reinterpret_cast<float4*>(o32 + 4 * i) = r;
+        if (olp) st4_any(olp, lp_dtype, 4 * i, r);
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+        const long long i = (n4 << 2) + threadIdx.x;
+        const float x = ld_any(a, a_dtype, i);
+        float r = x;
+        if (OP == EW_GELU) r = quick_gelu(x);
+        if (OP == EW_GELU_BWD) r = x * qgelu_grad(ld_any(b, b_dtype, i));
+        if (o32) o32[i] = r;
+        if (olp) st_any(olp, lp_dtype, i, r);
+    }
+}
+
+__global__ void __launch_bounds__(256) group_sum_kernel(const void* src, int src_dtype, long long groups, int alpha, long long inner, void* dst,
+                                                        int dst_dtype) {
+    const long long inner4 = inner >> 2, total = groups * inner4;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const long long g = idx / inner4, i = (idx - g * inner4) * 4;
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int k = 0; k < alpha; ++k) {
+            const float4 v = ld4_any(src, src_dtype, (g * alpha + k) * inner + i);
+            s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+        }
+        st4_any(dst, dst_dtype, g * inner + i, s);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// column sums: block = 32 columns x 8 row lanes; rows of all groups are split over blockIdx.y; one atomicAdd per
+// (block, column, period slot).  period > 1 (per-frame class tokens, positional embeddings) uses rows_per_group == 1.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) colsum_kernel(const void* src, int dtype, long long ld, long long groups, long long rows_per_group,
+                                                     long long gstride, long long roff, long long period, int cols, float* out,
+                                                     long long rows_per_block) {
+    __shared__ float red[8][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + tx;
+    const long long total = groups * rows_per_group;
+    const long long r_begin = (long long)blockIdx.y * rows_per_block;
+    long long r_end = r_begin + rows_per_block;
+    if (r_end > total) r_end = total;
+    if (period == 1) {
+        float s = 0.f;
+        if (c < cols)
+            for (long long i = r_begin + ty; i < r_end; i += 8) {
+                const long long g = i / rows_per_group, r = i - g * rows_per_group;
+                s += ld_any(src, dtype, (g * gstride + roff + r) * ld + c);
+            }
+        red[ty][tx] = s;
+        __syncthreads();
+        if (ty == 0 && c < cols) {
+            float t = 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) t += red[j][tx];
+            atomicAdd(out + c, t);
+        }
+    } else {
+        // slot p collects the groups g with g % period == p (rows_per_group rows each); blockIdx.y strides over p
+        for (long long p = blockIdx.y; p < period; p += gridDim.y) {
+            float s = 0.f;
+            if (c < cols)
+                for (long long g = p + (long long)ty * period; g < groups; g += 8 * period)
+                    for (long long r = 0; r < rows_per_group; ++r) s += ld_any(src, dtype, (g * gstride + roff + r) * ld + c);
+            red[ty][tx] = s;
+            __syncthreads();
+            if (ty == 0 && c < cols) {
+                float t = 0.f;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) t += red[j][tx];
+                atomicAdd(out + p * cols + c, t);
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// LayerNorm backward: one warp per row (row in registers, cols <= 1024), statistics recomputed; the parameter
+// gradients are reduced per block in shared memory (fp32 atomics within the block, then one global atomic per
+// column and block).
+// ---------------------------------------------------------------------------------------------------
+constexpr int LNB_MAXV = 8;
+constexpr int LNB_WARPS = 8;
+
+__global__ void __launch_bounds__(LNB_WARPS * 32) layernorm_bwd_kernel(
+    const float* __restrict__ in1, long long ld_in1, const float* __restrict__ in2, long long ld_in2, long long in2_period, long long rows, int cols,
+    float eps, const float* __restrict__ g1, const void* dy1, long long ld_dy1, const float* __restrict__ g2, const void* dy2, long long ld_dy2,
+    int dy_dtype, const float* add, long long ld_add, float* dx, long long ld_dx, int accumulate, void* dx_lp, long long ld_dx_lp, int lp_dtype,
+    float* dg1, float* db1, float* dg2, float* db2, int rows_per_warp) {
+    extern __shared__ float sh[];            // [4][cols]: dg1, db1, dg2, db2 partials of this block
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < 4 * cols; i += blockDim.x) sh[i] = 0.f;
+    __syncthreads();
+    float a_dg1[LNB_MAXV][4], a_db1[LNB_MAXV][4], a_dg2[LNB_MAXV][4], a_db2[LNB_MAXV][4];
+#pragma unroll
+    for (int i = 0; i < LNB_MAXV; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) a_dg1[i][j] = a_db1[i][j] = a_dg2[i][j] = a_db2[i][j] = 0.f;
+
+    const long long row_begin = ((long long)blockIdx.x * LNB_WARPS + warp) * rows_per_warp;
+    for (int rr = 0; rr < rows_per_warp; ++rr) {
+        const long long row = row_begin + rr;
+        if (row >= rows) break;
+        const float* x = in1 + row * ld_in1;
+        const float* x2 = in2 ? in2 + (row % in2_period) * ld_in2 : nullptr;
+        float4 v[LNB_MAXV];
+        float sum = 0.f;
+#pragma unroll
+        for (int i = 0; i < LNB_MAXV; ++i) {
+            const int c = (i * 32 + lane) * 4;
+            if (c < cols) {
+                v[i] = *reinterpret_cast<const float4*>(x + c);
+                if (x2) {
+                    const float4 w = *reinterpret_cast<const float4*>(x2 + c);
+                    v[i].x += w.x; v[i].y += w.y; v[i].z += w.z; v[i].w += w.w;
+                }
+                sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+            }
+        }
+        const float mean = warp_sum(sum) / (float)cols;
+        float sq = 0.f;
+#pragma unroll
+        for (int i = 0; i < LNB_MAXV; ++i) {
+            const int c = (i * 32 + lane) * 4;
+            if (c < cols) {
+                v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+                sq += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+            }
+        }
+        const float rstd = rsqrtf(warp_sum(sq) / (float)cols + eps);
+        // g = dy1*g1 + dy2*g2; accumulate parameter gradients; row means of g and g*xhat
+        float4 g[LNB_MAXV];
+        float sg = 0.f, sgx = 0.f;
+#pragma unroll
+        for (int i = 0; i < LNB_MAXV; ++i) {
+            const int c = (i * 32 + lane) * 4;
+            if (c < cols) {
+                v[i].x *= rstd; v[i].y *= rstd; v[i].z *= rstd; v[i].w *= rstd;          // xhat
+                const float4 d1 = ld4_any(dy1, dy_dtype, row * ld_dy1 + c);
+                const float4 ga = *reinterpret_cast<const float4*>(g1 + c);
+                g[i] = make_float4(d1.x * ga.x, d1.y * ga.y, d1.z * ga.z, d1.w * ga.w);
+                a_dg1[i][0] += d1.x * v[i].x; a_dg1[i][1] += d1.y * v[i].y; a_dg1[i][2] += d1.z * v[i].z; a_dg1[i][3] += d1.w * v[i].w;
+                a_db1[i][0] += d1.x; a_db1[i][1] += d1.y; a_db1[i][2] += d1.z; a_db1[i][3] += d1.w;
+                if (dy2) {
+                    const float4 d2 = ld4_any(dy2, dy_dtype, row * ld_dy2 + c);
+                    const float4 gb = *reinterpret_cast<const float4*>(g2 + c);
+                    g[i].x += d2.x * gb.x; g[i].y += d2.y * gb.y; g[i].z += d2.z * gb.z; g[i].w += d2.w * gb.w;
+                    a_dg2[i][0] += d2.x * v[i].x; a_dg2[i][1] += d2.y * v[i].y; a_dg2[i][2] += d2.z * v[i].z; a_dg2[i][3] += d2.w * v[i].w;
+                    a_db2[i][0] += d2.x; a_db2[i][1] += d2.y; a_db2[i][2] += d2.z; a_db2[i][3] += d2.w;
+                }
+                sg += (g[i].x + g[i].y) + (g[i].z + g[i].w);
+                sgx += (g[i].x * v[i].x + g[i].y * v[i].y) + (g[i].z * v[i].z + g[i].w * v[i].w);
+            }
+        }
+        const float mg = warp_sum(sg) / (float)cols, mgx = warp_sum(sgx) / (float)cols;
+#pragma unroll
+        for (int i = 0; i < LNB_MAXV; ++i) {
+            const int c = (i * 32 + lane) * 4;
+            if (c < cols) {
+                float4 o = make_float4(rstd * (g[i].x - mg - v[i].x * mgx), rstd * (g[i].y - mg - v[i].y * mgx),
+                                       rstd * (g[i].z - mg - v[i].z * mgx), rstd * (g[i].w - mg - v[i].w * mgx));
+                if (add) {
+                    const float4 a = *reinterpret_cast<const float4*>(add + row * ld_add + c);
+                    o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
+                }
+                if (dx) {
+                    float4* p = reinterpret_cast<float4*>(dx + row * ld_dx + c);
+                    if (accumulate) {
+                        const float4 a = *p;
+                        o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
+                    }
+                    *p = o;
+                }
+                if (dx_lp) st4_any(dx_lp, lp_dtype, row * ld_dx_lp + c, o);
+            }
+        }
+    }
+    // block reduction of the parameter gradients
+#pragma unroll
+    for (int i = 0; i < LNB_MAXV; ++i) {
+        const int c = (i * 32 + lane) * 4;
+        if (c < cols) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (dg1) atomicAdd(&sh[c + j], a_dg1[i][j]);
+                if (db1) atomicAdd(&sh[cols + c + j], a_db1[i][j]);
+                if (dg2) atomicAdd(&sh[2 * cols + c + j], a_dg2[i][j]);
+                if (db2) atomicAdd(&sh[3 * cols + c + j], a_db2[i][j]);
+            }
+        }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < cols; c += blockDim.x) {
+        if (dg1) atomicAdd(dg1 + c, sh[c]);
+        if (db1) atomicAdd(db1 + c, sh[cols + c]);
+        if (dg2) atomicAdd(dg2 + c, sh[2 * cols + c]);
+        if (db2) atomicAdd(db2 + c, sh[3 * cols + c]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// single-query cross-attention backward: one warp per (batch element, head), head dim 64, lanes own two dims.
+//   p = softmax(q.k / 8); dp_j = dO.v_j; ds_j = p_j (dp_j - sum_i p_i dp_i);
+//   dq = sum_j ds_j k_j / 8; dk_j = ds_j q / 8; dv_j = p_j dO
+// ---------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(128) cross_attention_bwd_kernel(const T* __restrict__ q, const T* __restrict__ kv, const T* __restrict__ d_out,
+                                                                  T* __restrict__ dq, T* __restrict__ dkv, int batch, int keys, int heads) {
+    extern __shared__ float sc_all[];          // per warp: [keys] probabilities, [keys] dp
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    const long long item = (long long)blockIdx.x * wpb + warp;
+    if (item >= (long long)batch * heads) return;
+    float* pr = sc_all + (size_t)warp * 2 * keys;
+    float* dp = pr + keys;
+    const int b = (int)(item / heads), h = (int)(item % heads), C = heads * 64;
+    const long long qoff = (long long)b * C + h * 64 + lane * 2;
+    const float q0 = to_float(q[qoff]), q1 = to_float(q[qoff + 1]);
+    const float o0 = to_float(d_out[qoff]), o1 = to_float(d_out[qoff + 1]);
+    const T* kbase = kv + (long long)b * keys * 2 * C + h * 64 + lane * 2;
+    float mx = -INFINITY;
+    for (int j = 0; j < keys; ++j) {
+        const T* kp = kbase + (long long)j * 2 * C;
+        const float s = warp_sum(q0 * to_float(kp[0]) + q1 * to_float(kp[1])) * 0.125f;
+        const float d = warp_sum(o0 * to_float(kp[C]) + o1 * to_float(kp[C + 1]));
+        if (lane == 0) { pr[j] = s; dp[j] = d; }
+        mx = fmaxf(mx, s);
+    }
+    __syncwarp();
+    float den = 0.f;
+    for (int j = lane; j < keys; j += 32) {
+        const float e = __expf(pr[j] - mx);
+        pr[j] = e;
+        den += e;
+    }
+    den = warp_sum(den);
+    __syncwarp();
+    const float inv = 1.f / den;
+    float dot = 0.f;
+    for (int j = lane; j < keys; j += 32) {
+        pr[j] *= inv;
+        dot += pr[j] * dp[j];
+    }
+    dot = warp_sum(dot);
+    __syncwarp();
+    float dq0 = 0.f, dq1 = 0.f;
+    T* dbase = dkv + (long long)b * keys * 2 * C + h * 64 + lane * 2;
+    for (int j = 0; j < keys; ++j) {
+        const float p = pr[j];
+        const float ds = p * (dp[j] - dot) * 0.125f;
+        const T* kp = kbase + (long long)j * 2 * C;
+        dq0 = fmaf(ds, to_float(kp[0]), dq0);
+        dq1 = fmaf(ds, to_float(kp[1]), dq1);
+        T* dk = dbase + (long long)j * 2 * C;
+        dk[0] = from_float<T>(ds * q0);
+        dk[1] = from_float<T>(ds * q1);
+        dk[C] = from_float<T>(p * o0);
+        dk[C + 1] = from_float<T>(p * o1);
+    }
+    dq[qoff] = from_float<T>(dq0);
+    dq[qoff + 1] = from_float<T>(dq1);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// train-mode head + soft-target cross entropy: one block per clip.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float block_sum(float v, float* red, int tid) {
+    const int lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    float t = 0.f;
+    for (int w = 0; w < nw; ++w) t += red[w];
+    return t;
+}
+__device__ __forceinline__ float block_max(float v, float* red, int tid) {
+    const int lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+    v = warp_max(v);
+    __syncthreads();
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    float t = red[0];
+    for (int w = 1; w < nw; ++w) t = fmaxf(t, red[w]);
+    return t;
+}
+
+__global__ void __launch_bounds__(256) softce_head_kernel(const float* __restrict__ emb, const float* __restrict__ text_n, float scale,
+                                                          const float* __restrict__ target, int batch, int E, int C, float* logits, float* loss,
+                                                          float* d_emb) {
+    extern __shared__ float sh[];          // [E] unit embedding, [C] logits -> d_logits, [E] u = d_logits . text_n, [32] scratch
+    float* se = sh;
+    float* sl = sh + E;
+    float* su = sl + C;
+    float* red = su + E;
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+    float ss = 0.f;
+    for (int e = tid; e < E; e += blockDim.x) {
+        const float v = emb[(long long)b * E + e];
+        se[e] = v;
+        ss += v * v;
+    }
+    const float inv_norm = rsqrtf(block_sum(ss, red, tid));
+    for (int e = tid; e < E; e += blockDim.x) se[e] *= inv_norm;
+    __syncthreads();
+    for (int c = warp; c < C; c += nw) {
+        float dot = 0.f;
+        for (int e = lane; e < E; e += 32) dot = fmaf(se[e], text_n[(long long)c * E + e], dot);
+        dot = warp_sum(dot);
+        if (lane == 0) {
+            sl[c] = dot * scale;
+            if (logits) logits[(long long)b * C + c] = dot * scale;
+        }
+    }
+    __syncthreads();
+    float mx = -INFINITY;
+    for (int c = tid; c < C; c += blockDim.x) mx = fmaxf(mx, sl[c]);
+    mx = block_max(mx, red, tid);
+    float den = 0.f, tsum = 0.f, tl = 0.f;
+    for (int c = tid; c < C; c += blockDim.x) {
+        den += __expf(sl[c] - mx);
+        const float t = target[(long long)b * C + c];
+        tsum += t;
+        tl += t * sl[c];
+    }
+    den = block_sum(den, red, tid);
+    tsum = block_sum(tsum, red, tid);
+    tl = block_sum(tl, red, tid);
+    const float lse = mx + __logf(den);
+    if (tid == 0) atomicAdd(loss, (tsum * lse - tl) / (float)batch);       // sum_c -t_c (l_c - lse)
+    __syncthreads();
+    // d loss / d logits = (softmax * sum(t) - t) / batch
+    for (int c = tid; c < C; c += blockDim.x)
+        sl[c] = (__expf(sl[c] - lse) * tsum - target[(long long)b * C + c]) / (float)batch;
+    __syncthreads();
+    // u = scale * d_logits . text_n ; d_emb = (u - ehat (ehat . u)) / |emb|
+    float eu = 0.f;
+    for (int e = tid; e < E; e += blockDim.x) {
+        float u = 0.f;
+        for (int c = 0; c < C; ++c) u = fmaf(sl[c], text_n[(long long)c * E + e], u);
+        u *= scale;
+        su[e] = u;
+        eu += u * se[e];
+    }
+    eu = block_sum(eu, red, tid);
+    for (int e = tid; e < E; e += blockDim.x) d_emb[(long long)b * E + e] = (su[e] - se[e] * eu) * inv_norm;
+}
+
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                                                    long long n, float lr, float beta1, float beta2, float eps, float decay, float inv_bc1,
+                                                    float inv_sqrt_bc2, float grad_scale) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float gi = g[i] * grad_scale;
+        const float mi = beta1 * m[i] + (1.f - beta1) * gi;
+        const float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
+        m[i] = mi;
+        v[i] = vi;
+        const float denom = sqrtf(vi) * inv_sqrt_bc2 + eps;
+        p[i] = p[i] * decay - lr * inv_bc1 * mi / denom;
+    }
+}
+
+// operand copies: 32x32 tiles through shared memory so that both the straight and the transposed copy are coalesced
+template <typename T>
+__global__ void __launch_bounds__(256) pack_weight_kernel(const float* __restrict__ w, int n, int k, T* out, long long ld_out, T* out_t,
+                                                          long long ld_out_t) {
+    __shared__ float tile[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const long long bz = blockIdx.z;
+    const float* src = w + bz * (long long)n * k;
+    const int n0 = blockIdx.y * 32, k0 = blockIdx.x * 32;
+    for (int i = ty; i < 32; i += 8) {
+        const int nn = n0 + i, kk = k0 + tx;
+        const float v = (nn < n && kk < k) ? src[(long long)nn * k + kk] : 0.f;
+        tile[i][tx] = v;
+        if (out && nn < n && kk < ld_out) out[bz * n * ld_out + (long long)nn * ld_out + kk] = from_float<T>(v);
+    }
+    __syncthreads();
+    if (out_t)
+        for (int i = ty; i < 32; i += 8) {
+            const int kk = k0 + i, nn = n0 + tx;
+            if (kk < k && nn < ld_out_t) out_t[bz * k * ld_out_t + (long long)kk * ld_out_t + nn] = from_float<T>(nn < n ? tile[tx][i] : 0.f);
+        }
+}
+
+}  // namespace
+
+}  // namespace distb200
+
+using namespace distb200;
+
+#define DISTB200_DTYPE_OK(dt) ((dt) == DISTB200_F32 || (dt) == DISTB200_BF16)
+
+extern "C" int distb200_quickgelu(const void* z, int32_t z_dtype, float* y_f32, void* y_lp, int32_t lp_dtype, int64_t n, void* stream) {
+    if (n == 0) return 0;
+    DISTB200_REQUIRE(z && (y_f32 || y_lp) && DISTB200_DTYPE_OK(z_dtype) && DISTB200_DTYPE_OK(lp_dtype), "quickgelu: bad arguments");
+    elementwise_kernel<EW_GELU><<<grid_cap(n / 4 + 1, 256), 256, 0, (cudaStream_t)stream>>>(z, z_dtype, nullptr, 0, y_f32, y_lp, lp_dtype, n);
+    return check_launch("quickgelu");
+}
+
+extern "C" int distb200_quickgelu_bwd(const void* dy, int32_t dy_dtype, const void* z, int32_t z_dtype, float* dz_f32, void* dz_lp,
+                                      int32_t lp_dtype, int64_t n, void* stream) {
+    if (n == 0) return 0;
+    DISTB200_REQUIRE(dy && z && (dz_f32 || dz_lp) && DISTB200_DTYPE_OK(dy_dtype) && DISTB200_DTYPE_OK(z_dtype) && DISTB200_DTYPE_OK(lp_dtype),
+                    "quickgelu_bwd: bad arguments");
+    elementwise_kernel<EW_GELU_BWD><<<grid_cap(n / 4 + 1, 256), 256, 0, (cudaStream_t)stream>>>(dy, dy_dtype, z, z_dtype, dz_f32, dz_lp, lp_dtype, n);
+    return check_launch("quickgelu_bwd");
+}
+
+extern "C" int distb200_cast(const float* src, void* dst, int32_t dst_dtype, int64_t n, void* stream) {
+    if (n == 0) return 0;
+    DISTB200_REQUIRE(src && dst && DISTB200_DTYPE_OK(dst_dtype), "cast: bad arguments");
+    elementwise_kernel<EW_CAST><<<grid_cap(n / 4 + 1, 256), 256, 0, (cudaStream_t)stream>>>(src, DISTB200_F32, nullptr, 0, nullptr, dst, dst_dtype, n);
+    return check_launch("cast");
+}
+
+extern "C" int distb200_group_sum(const void* src, int32_t src_dtype, int64_t groups, int32_t alpha, int64_t inner, void* dst,
+                                  int32_t dst_dtype, void* stream) {
+    if (groups == 0 || inner == 0) return 0;
+    DISTB200_REQUIRE(src && dst && alpha >= 1 && inner % 4 == 0 && DISTB200_DTYPE_OK(src_dtype) && DISTB200_DTYPE_OK(dst_dtype),
+                    "group_sum: bad arguments (inner must be a multiple of 4)");
+    group_sum_kernel<<<grid_cap(groups * inner / 4, 256), 256, 0, (cudaStream_t)stream>>>(src, src_dtype, groups, alpha, inner, dst, dst_dtype);
+    return check_launch("group_sum");
+}
+
+extern "C" int distb200_colsum(const void* src, int32_t src_dtype, int64_t ld, int64_t groups, int64_t rows_per_group, int64_t gstride,
+                               int64_t roff, int64_t period, int32_t cols, float* out, void* stream) {
+    if (groups == 0 || rows_per_group == 0 || cols == 0) return 0;
+    DISTB200_REQUIRE(src && out && period >= 1 && DISTB200_DTYPE_OK(src_dtype), "colsum: bad arguments");
+    const long long total = groups * rows_per_group;
+    dim3 grid((unsigned)((cols + 31) / 32), 1);
+    long long rows_per_block = total;
+    if (period == 1) {
+        long long splits = (long long)sm_count() * 4 / grid.x;
+        if (splits < 1) splits = 1;
+        rows_per_block = (total + splits - 1) / splits;
+        if (rows_per_block < 64) rows_per_block = 64;
+        grid.y = (unsigned)((total + rows_per_block - 1) / rows_per_block);
+    } else {
+        grid.y = (unsigned)(period < 65535 ? period : 65535);
+    }
+    colsum_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, src_dtype, ld, groups, rows_per_group, gstride, roff, period, cols, out, rows_per_block);
+    return check_launch("colsum");
+}
+
+extern "C" int distb200_layernorm_bwd(const float* in1, int64_t ld_in1, const float* in2, int64_t ld_in2, int64_t in2_period, int64_t rows,
+                                      int32_t cols, float eps, const float* g1, const void* dy1, int64_t ld_dy1, const float* g2,
+                                      const void* dy2, int64_t ld_dy2, int32_t dy_dtype, const float* add, int64_t ld_add, float* dx,
+                                      int64_t ld_dx, int32_t accumulate, void* dx_lp, int64_t ld_dx_lp, int32_t lp_dtype, float* dg1,
+                                      float* db1, float* dg2, float* db2, void* stream) {
+    if (rows == 0) return 0;
+    DISTB200_REQUIRE(cols % 4 == 0 && cols <= 128 * LNB_MAXV, "layernorm_bwd: cols=%d must be a multiple of 4 and <= %d", cols, 128 * LNB_MAXV);
+    DISTB200_REQUIRE(in1 && g1 && dy1 && (dx || dx_lp), "layernorm_bwd: null pointer");
+    DISTB200_REQUIRE(!dy2 || g2, "layernorm_bwd: second affine parameters missing");
+    DISTB200_REQUIRE(ld_in1 % 4 == 0 && ld_dy1 % 4 == 0 && (!dy2 || ld_dy2 % 4 == 0) && (!in2 || ld_in2 % 4 == 0) && (!add || ld_add % 4 == 0) &&
+                        (!dx || ld_dx % 4 == 0) && (!dx_lp || ld_dx_lp % 4 == 0),
+                    "layernorm_bwd: row pitches must be multiples of 4");
+    DISTB200_REQUIRE(DISTB200_DTYPE_OK(dy_dtype) && DISTB200_DTYPE_OK(lp_dtype), "layernorm_bwd: bad dtype");
+    if (!in2) in2_period = 1;
+    DISTB200_REQUIRE(in2_period >= 1, "layernorm_bwd: in2_period must be >= 1");
+    // enough rows per warp to amortise the block-level parameter-gradient reduction, enough blocks to fill the GPU
+    long long warps = (long long)sm_count() * 4 * LNB_WARPS;
+    int rows_per_warp = (int)((rows + warps - 1) / warps);
+    if (rows_per_warp < 1) rows_per_warp = 1;
+    const long long blocks = (rows + (long long)LNB_WARPS * rows_per_warp - 1) / ((long long)LNB_WARPS * rows_per_warp);
+    const size_t smem = (size_t)4 * cols * sizeof(float);
+    layernorm_bwd_kernel<<<(unsigned)blocks, LNB_WARPS * 32, smem, (cudaStream_t)stream>>>(
+        in1, ld_in1, in2, ld_in2, in2_period, rows, cols, eps, g1, dy1, ld_dy1, g2, dy2, ld_dy2, dy_dtype, add, ld_add, dx, ld_dx, accumulate, dx_lp,
+        ld_dx_lp, lp_dtype, dg1, db1, dg2, db2, rows_per_warp);
+    return check_launch("layernorm_bwd");
+}
+
+extern "C" int distb200_cross_attention_bwd(const void* q, const void* kv, const void* d_out, void* dq, void* dkv, int32_t batch, int32_t keys,
+                                            int32_t heads, int32_t dtype, void* stream) {
+    if (batch == 0) return 0;
+    DISTB200_REQUIRE(q && kv && d_out && dq && dkv, "cross_attention_bwd: null pointer");
+    DISTB200_REQUIRE(keys >= 1 && keys <= 2048, "cross_attention_bwd: keys=%d out of range", keys);
+    const int wpb = 4;
+    const long long items = (long long)batch * heads;
+    const unsigned grid = (unsigned)((items + wpb - 1) / wpb);
+    const size_t smem = (size_t)wpb * 2 * keys * sizeof(float);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == DISTB200_F32)
+        cross_attention_bwd_kernel<float><<<grid, wpb * 32, smem, st>>>((const float*)q, (const float*)kv, (const float*)d_out, (float*)dq, (float*)dkv, batch, keys, heads);
+    else
+        cross_attention_bwd_kernel<bf16><<<grid, wpb * 32, smem, st>>>((const bf16*)q, (const bf16*)kv, (const bf16*)d_out, (bf16*)dq, (bf16*)dkv, batch, keys, heads);
+    return check_launch("cross_attention_bwd");
+}
+
+extern "C" int distb200_softce_head(const float* emb, const float* text_n, float scale, const float* target, int32_t batch, int32_t embed_dim,
+                                    int32_t classes, float* logits, float* loss, float* d_emb, void* stream) {
+    if (batch == 0) return 0;
+    DISTB200_REQUIRE(emb && text_n && target && loss && d_emb, "softce_head: null pointer");
+    const size_t smem = (size_t)(2 * embed_dim + classes + 32) * sizeof(float);
+    DISTB200_REQUIRE(smem <= 48 * 1024, "softce_head: E + C too large for one block (%zu bytes)", smem);
+    softce_head_kernel<<<batch, 256, smem, (cudaStream_t)stream>>>(emb, text_n, scale, target, batch, embed_dim, classes, logits, loss, d_emb);
+    return check_launch("softce_head");
+}
+
+extern "C" int distb200_adamw(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+                              float weight_decay, int32_t step, float grad_scale, void* stream) {
+    if (n == 0) return 0;
+    DISTB200_REQUIRE(p && g && m && v && step >= 1, "adamw: bad arguments");
+    const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
+    adamw_kernel<<<grid_cap(n, 256), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, 1.0f - lr * weight_decay, (float)(1.0 / bc1),
+                                                                    (float)(1.0 / sqrt(bc2)), grad_scale);
+    return check_launch("adamw");
+}
+
+extern "C" int distb200_pack_weight(const float* w, int64_t batch, int32_t n, int32_t k, void* out, int64_t ld_out, void* out_t,
+                                    int64_t ld_out_t, int32_t dtype, void* stream) {
+    if (batch == 0 || n == 0 || k == 0) return 0;
+    DISTB200_REQUIRE(w && (out || out_t) && DISTB200_DTYPE_OK(dtype), "pack_weight: bad arguments");
+    DISTB200_REQUIRE((!out || ld_out >= k) && (!out_t || ld_out_t >= n), "pack_weight: row pitch too small");
+    const long long kc = out ? (ld_out > k ? ld_out : k) : k, nc = out_t ? (ld_out_t > n ? ld_out_t : n) : n;
+    dim3 grid((unsigned)((kc + 31) / 32), (unsigned)((nc + 31) / 32), (unsigned)batch);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == DISTB200_F32) pack_weight_kernel<float><<<grid, 256, 0, st>>>(w, n, k, (float*)out, ld_out, (float*)out_t, ld_out_t);
+    else pack_weight_kernel<bf16><<<grid, 256, 0, st>>>(w, n, k, (bf16*)out, ld_out, (bf16*)out_t, ld_out_t);
+    return check_launch("pack_weight");
+}

@@ -41,6 +41,22 @@ class GemmDesc(C.Structure):
     ]
 
 
+class WgradDesc(C.Structure):
+    """Mirror of ``distb200_wgrad_desc``."""
+    _fields_ = [
+        ("x", C.c_void_p), ("dy", C.c_void_p),
+        ("dtype", C.c_int32), ("impl", C.c_int32),
+        ("a_dim", C.c_int64 * 4), ("a_stride", C.c_int64 * 4),
+        ("img_w", C.c_int32), ("num_taps", C.c_int32),
+        ("tap_off", (C.c_int32 * 3) * MAX_TAPS),
+        ("n", C.c_int32), ("k", C.c_int32),
+        ("groups", C.c_int64), ("rows_per_group", C.c_int64),
+        ("group_dim", C.c_int32), ("reserved", C.c_int32),
+        ("ld_dy", C.c_int64), ("dy_gstride", C.c_int64), ("dy_roff", C.c_int64),
+        ("dw", C.c_void_p), ("ld_dw", C.c_int64), ("dw_tap_stride", C.c_int64),
+    ]
+
+
 _LIB = None
 
 
@@ -74,6 +90,21 @@ def lib():
     L.distb200_rows_bcast.argtypes = [vp, i64, i64, i32, vp, i64, i32, vp]
     L.distb200_mean_rows.argtypes = [vp, i64, i32, i64, i32, vp, i32, vp]
     L.distb200_class_head.argtypes = [vp, vp, f32, i32, i32, i32, vp, vp, vp]
+    # fine-tuning step
+    L.distb200_gemm_wgrad.argtypes = [C.POINTER(WgradDesc), vp]
+    L.distb200_quickgelu.argtypes = [vp, i32, vp, vp, i32, i64, vp]
+    L.distb200_quickgelu_bwd.argtypes = [vp, i32, vp, i32, vp, vp, i32, i64, vp]
+    L.distb200_cast.argtypes = [vp, vp, i32, i64, vp]
+    L.distb200_group_sum.argtypes = [vp, i32, i64, i32, i64, vp, i32, vp]
+    L.distb200_colsum.argtypes = [vp, i32, i64, i64, i64, i64, i64, i64, i32, vp, vp]
+    L.distb200_layernorm_bwd.argtypes = [vp, i64, vp, i64, i64, i64, i32, f32, vp, vp, i64, vp, vp, i64, i32, vp, i64, vp, i64, i32,
+                                         vp, i64, i32, vp, vp, vp, vp, vp]
+    L.distb200_cross_attention_bwd.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]
+    L.distb200_softce_head.argtypes = [vp, vp, f32, vp, i32, i32, i32, vp, vp, vp, vp]
+    L.distb200_adamw.argtypes = [vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, i32, f32, vp]
+    L.distb200_pack_weight.argtypes = [vp, i64, i32, i32, vp, i64, vp, i64, i32, vp]
+    for name in TRAIN_EXPORTS:
+        getattr(L, name).restype = C.c_int
     for name in ("gemm", "layernorm", "attention", "cross_attention", "patchify", "rows_bcast", "mean_rows", "class_head"):
         getattr(L, "distb200_" + name).restype = C.c_int
     assert L.distb200_version() == 100 and L.distb200_arch() == 100
@@ -81,7 +112,11 @@ def lib():
     return L
 
 
-EXPORTS = ("distb200_version", "distb200_arch", "distb200_last_error", "distb200_gemm", "distb200_layernorm",
+TRAIN_EXPORTS = ("distb200_gemm_wgrad", "distb200_quickgelu", "distb200_quickgelu_bwd", "distb200_cast", "distb200_group_sum",
+                 "distb200_colsum", "distb200_layernorm_bwd", "distb200_cross_attention_bwd", "distb200_softce_head",
+                 "distb200_adamw", "distb200_pack_weight")
+
+EXPORTS = TRAIN_EXPORTS + ("distb200_version", "distb200_arch", "distb200_last_error", "distb200_gemm", "distb200_layernorm",
            "distb200_attention", "distb200_cross_attention", "distb200_patchify", "distb200_rows_bcast",
            "distb200_mean_rows", "distb200_class_head")
 
@@ -228,3 +263,117 @@ def mean_rows(src, row_stride, count, batch, cols, out, name="mean_rows"):
 def class_head(emb, text_n, scale, batch, embed_dim, classes, logits, probs, name="class_head"):
     args = (emb.data_ptr(), text_n.data_ptr(), float(scale), int(batch), int(embed_dim), int(classes), _ptr(logits), _ptr(probs))
     return Call(lib().distb200_class_head, args, name, keep=(emb, text_n, logits, probs))
+
+
+# ---- fine-tuning step ------------------------------------------------------------------------------
+
+def wgrad(x, dy, dw, n, k, *, a_dim=None, a_stride=None, taps=((0, 0, 0),), img_w=0, groups=1, rows_per_group=None, group_dim=2,
+          ld_dy=None, dy_gstride=None, dy_roff=0, ld_dw=None, dw_tap_stride=None, impl=IMPL_AUTO, name="wgrad"):
+    """Prepare ``distb200_gemm_wgrad``: dw[tap, n, k] += sum_rows dy[row, n] * A_tap(row, k) (A addressed as in :func:`gemm`)."""
+    d = WgradDesc()
+    assert x.dtype == dy.dtype and dw.dtype == torch.float32
+    d.x, d.dy, d.dw = x.data_ptr(), dy.data_ptr(), dw.data_ptr()
+    d.dtype, d.impl = enum_of(x), impl
+    if a_dim is None:
+        assert x.dim() == 2 and x.stride(1) == 1
+        a_dim = (k, x.shape[0], 1, 1)
+        a_stride = (1, x.stride(0), x.stride(0) * x.shape[0], x.stride(0) * x.shape[0])
+        if rows_per_group is None:
+            rows_per_group = x.shape[0]
+    for i in range(4):
+        d.a_dim[i], d.a_stride[i] = int(a_dim[i]), int(a_stride[i])
+    d.img_w, d.num_taps = int(img_w), len(taps)
+    for j, tp in enumerate(taps):
+        for i in range(3):
+            d.tap_off[j][i] = int(tp[i])
+    d.n, d.k = int(n), int(k)
+    d.groups, d.rows_per_group, d.group_dim = int(groups), int(rows_per_group), int(group_dim)
+    d.ld_dy = int(ld_dy if ld_dy is not None else n)
+    d.dy_gstride = int(dy_gstride if dy_gstride is not None else rows_per_group)
+    d.dy_roff = int(dy_roff)
+    d.ld_dw = int(ld_dw if ld_dw is not None else k)
+    d.dw_tap_stride = int(dw_tap_stride if dw_tap_stride is not None else int(n) * d.ld_dw)
+    rows = int(groups) * int(rows_per_group)
+    flops = 2 * rows * int(n) * int(k) * len(taps)
+    nbytes = rows * (int(n) + int(k)) * x.element_size()
+    return Call(lib().distb200_gemm_wgrad, (C.byref(d),), name, keep=(d, x, dy, dw), flops=flops, nbytes=nbytes)
+
+
+def quickgelu(z, y_f32=None, y_lp=None, n=None, name="quickgelu"):
+    n = int(n if n is not None else z.numel())
+    args = (z.data_ptr(), enum_of(z), _ptr(y_f32), _ptr(y_lp), enum_of(y_lp) if y_lp is not None else F32, n)
+    nb = n * (z.element_size() + (4 if y_f32 is not None else 0) + (y_lp.element_size() if y_lp is not None else 0))
+    return Call(lib().distb200_quickgelu, args, name, keep=(z, y_f32, y_lp), nbytes=nb)
+
+
+def quickgelu_bwd(dy, z, dz_f32=None, dz_lp=None, n=None, name="quickgelu_bwd"):
+    n = int(n if n is not None else z.numel())
+    args = (dy.data_ptr(), enum_of(dy), z.data_ptr(), enum_of(z), _ptr(dz_f32), _ptr(dz_lp), enum_of(dz_lp) if dz_lp is not None else F32, n)
+    nb = n * (dy.element_size() + z.element_size() + (4 if dz_f32 is not None else 0) + (dz_lp.element_size() if dz_lp is not None else 0))
+    return Call(lib().distb200_quickgelu_bwd, args, name, keep=(dy, z, dz_f32, dz_lp), nbytes=nb)
+
+
+def cast(src, dst, n=None, name="cast"):
+    assert src.dtype == torch.float32
+    n = int(n if n is not None else src.numel())
+    return Call(lib().distb200_cast, (src.data_ptr(), dst.data_ptr(), enum_of(dst), n), name, keep=(src, dst), nbytes=n * (4 + dst.element_size()))
+
+
+def group_sum(src, dst, groups, alpha, inner, name="group_sum"):
+    args = (src.data_ptr(), enum_of(src), int(groups), int(alpha), int(inner), dst.data_ptr(), enum_of(dst))
+    return Call(lib().distb200_group_sum, args, name, keep=(src, dst), nbytes=groups * inner * (alpha * src.element_size() + dst.element_size()))
+
+
+def colsum(src, out, cols, *, ld=None, groups=1, rows_per_group=None, gstride=None, roff=0, period=1, name="colsum"):
+    assert out.dtype == torch.float32
+    ld = int(ld if ld is not None else cols)
+    if rows_per_group is None:
+        rows_per_group = src.numel() // ld
+    gstride = int(gstride if gstride is not None else rows_per_group)
+    args = (src.data_ptr(), enum_of(src), ld, int(groups), int(rows_per_group), gstride, int(roff), int(period), int(cols), out.data_ptr())
+    return Call(lib().distb200_colsum, args, name, keep=(src, out), nbytes=int(groups) * int(rows_per_group) * int(cols) * src.element_size())
+
+
+def layernorm_bwd(x, g1, dy1, *, rows=None, cols=None, in2=None, in2_period=1, g2=None, dy2=None, add=None, dx=None, accumulate=False,
+                  dx_lp=None, dg1=None, db1=None, dg2=None, db2=None, eps=1e-5, ld_x=None, ld_in2=None, ld_dy1=None, ld_dy2=None,
+                  ld_add=None, ld_dx=None, ld_dx_lp=None, name="layernorm_bwd"):
+    assert x.dtype == torch.float32
+    cols = int(cols if cols is not None else x.shape[-1])
+    rows = int(rows if rows is not None else x.numel() // cols)
+    d = lambda v: int(v if v is not None else cols)
+    if dy2 is not None:
+        assert dy2.dtype == dy1.dtype
+    args = (x.data_ptr(), d(ld_x), _ptr(in2), d(ld_in2), int(in2_period), rows, cols, float(eps),
+            g1.data_ptr(), dy1.data_ptr(), d(ld_dy1), _ptr(g2), _ptr(dy2), d(ld_dy2), enum_of(dy1),
+            _ptr(add), d(ld_add), _ptr(dx), d(ld_dx), int(bool(accumulate)),
+            _ptr(dx_lp), d(ld_dx_lp), enum_of(dx_lp) if dx_lp is not None else F32,
+            _ptr(dg1), _ptr(db1), _ptr(dg2), _ptr(db2))
+    nb = rows * cols * (4 + dy1.element_size() * (2 if dy2 is not None else 1) + (4 if dx is not None else 0))
+    return Call(lib().distb200_layernorm_bwd, args, name, keep=(x, in2, g1, dy1, g2, dy2, add, dx, dx_lp, dg1, db1, dg2, db2), nbytes=nb)
+
+
+def cross_attention_bwd(q, kv, d_out, dq, dkv, batch, keys, heads, name="cross_attention_bwd"):
+    assert q.dtype == kv.dtype == d_out.dtype == dq.dtype == dkv.dtype
+    args = (q.data_ptr(), kv.data_ptr(), d_out.data_ptr(), dq.data_ptr(), dkv.data_ptr(), int(batch), int(keys), int(heads), enum_of(q))
+    return Call(lib().distb200_cross_attention_bwd, args, name, keep=(q, kv, d_out, dq, dkv),
+                nbytes=batch * keys * heads * 256 * q.element_size())
+
+
+def softce_head(emb, text_n, scale, target, batch, embed_dim, classes, logits, loss, d_emb, name="softce_head"):
+    args = (emb.data_ptr(), text_n.data_ptr(), float(scale), target.data_ptr(), int(batch), int(embed_dim), int(classes),
+            _ptr(logits), loss.data_ptr(), d_emb.data_ptr())
+    return Call(lib().distb200_softce_head, args, name, keep=(emb, text_n, target, logits, loss, d_emb))
+
+
+def pack_weight(w, batch, n, k, out=None, out_t=None, ld_out=None, ld_out_t=None, name="pack_weight"):
+    assert w.dtype == torch.float32
+    ref = out if out is not None else out_t
+    args = (w.data_ptr(), int(batch), int(n), int(k), _ptr(out), int(ld_out if ld_out is not None else k), _ptr(out_t),
+            int(ld_out_t if ld_out_t is not None else n), enum_of(ref))
+    return Call(lib().distb200_pack_weight, args, name, keep=(w, out, out_t), nbytes=int(batch) * n * k * (4 + 2 * ref.element_size()))
+
+
+def adamw(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, step, grad_scale, stream):
+    """Immediate launch (the scalar arguments change every step)."""
+    _check(lib().distb200_adamw(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), int(n), float(lr), float(beta1), float(beta2),
+                                float(eps), float(weight_decay), int(step), float(grad_scale), stream), "adamw")

@@ -145,6 +145,100 @@ int distb200_mean_rows(const float* src, int64_t row_stride, int32_t count, int6
 int distb200_class_head(const float* emb, const float* text_n, float scale, int32_t batch, int32_t embed_dim,
                         int32_t classes, float* logits, float* probs, void* stream);
 
+
+/* ================================================================================================
+ * Fine-tuning step (runs/train.py:97-112): the reference gets the backward of
+ * the DiST branches from autograd (ATen kernels), the loss from models/utils/losses.py:20-31 and the update
+ * from torch.optim.AdamW (models/utils/optimizer.py:67-73).  The entry points below are the operators that
+ * replace those calls.  Gradients with respect to parameters are always ACCUMULATED (+=) into fp32 buffers
+ * the caller zeroes once per step, so that tied uses and split reductions compose.
+ * ================================================================================================ */
+
+/* Input gradient of distb200_gemm needs no entry point of its own: it is distb200_gemm with a = dY, the tap
+ * offsets negated and b = the per-tap transposed weights (distb200_pack_weight writes them). */
+
+/* Weight gradient of distb200_gemm (nn.Linear / nn.Conv3d weight.grad):
+ *     dw[j*dw_tap_stride + n*ld_dw + k] += sum_{gi, r} dy[(gi*dy_gstride + dy_roff + r)*ld_dy + n] * A_j(gi, r, k)
+ * with A_j(gi, r, k) exactly as defined for distb200_gemm (same a_dim / a_stride / tap_off / img_w / group_dim),
+ * j < num_taps, n < n, k < k.  x and dy have dtype `dtype` (bf16: tcgen05 tensor cores with both operands
+ * MN-major, split over row blocks with fp32 reductions into dw; fp32: FFMA).  impl as for distb200_gemm. */
+typedef struct distb200_wgrad_desc {
+    const void* x;
+    const void* dy;
+    int32_t dtype;
+    int32_t impl;
+    int64_t a_dim[4];
+    int64_t a_stride[4];
+    int32_t img_w;
+    int32_t num_taps;
+    int32_t tap_off[DISTB200_MAX_TAPS][3];
+    int32_t n;
+    int32_t k;
+    int64_t groups;
+    int64_t rows_per_group;
+    int32_t group_dim;
+    int32_t reserved;
+    int64_t ld_dy, dy_gstride, dy_roff;
+    float*  dw;
+    int64_t ld_dw, dw_tap_stride;
+} distb200_wgrad_desc;
+
+int distb200_gemm_wgrad(const distb200_wgrad_desc* desc, void* stream);
+
+/* QuickGELU on a saved pre-activation (training keeps z for the backward): y = z * sigmoid(1.702 z) written as fp32
+ * (y_f32) and / or in lp_dtype (y_lp); either may be NULL.  clip.py:199-201. */
+int distb200_quickgelu(const void* z, int32_t z_dtype, float* y_f32, void* y_lp, int32_t lp_dtype, int64_t n, void* stream);
+
+/* dz = dy * d/dz [z sigmoid(1.702 z)] = dy * s * (1 + 1.702 z (1 - s)), s = sigmoid(1.702 z). */
+int distb200_quickgelu_bwd(const void* dy, int32_t dy_dtype, const void* z, int32_t z_dtype, float* dz_f32, void* dz_lp,
+                           int32_t lp_dtype, int64_t n, void* stream);
+
+/* dst = (dst_dtype) src, n contiguous elements (the low-precision operand copy of an fp32 gradient). */
+int distb200_cast(const float* src, void* dst, int32_t dst_dtype, int64_t n, void* stream);
+
+/* dst[g*inner + i] = sum_{k < alpha} src[(g*alpha + k)*inner + i]: gradient of the nearest upsample along time
+ * (dist.py:105) - each sparse frame collects its alpha dense frames. */
+int distb200_group_sum(const void* src, int32_t src_dtype, int64_t groups, int32_t alpha, int64_t inner, void* dst,
+                       int32_t dst_dtype, void* stream);
+
+/* out[(g % period)*cols + c] += sum_{r < rows_per_group} src[(g*gstride + roff + r)*ld + c]   (bias.grad, cls_token.grad,
+ * positional_embedding.grad, aggregated token grads). */
+int distb200_colsum(const void* src, int32_t src_dtype, int64_t ld, int64_t groups, int64_t rows_per_group, int64_t gstride,
+                    int64_t roff, int64_t period, int32_t cols, float* out, void* stream);
+
+/* Backward of distb200_layernorm for x = in1 (+ in2[row % in2_period]); statistics are recomputed from x.
+ *   dx_row = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy1 * g1 (+ dy2 * g2)
+ *   dx (= or +=, `accumulate`) add[row] + dx_row;   dx_lp, when non-NULL, receives the final dx in lp_dtype
+ *   dg1 += sum_rows dy1 * xhat, db1 += sum_rows dy1 (dg2 / db2 alike; all optional). */
+int distb200_layernorm_bwd(const float* in1, int64_t ld_in1, const float* in2, int64_t ld_in2, int64_t in2_period,
+                           int64_t rows, int32_t cols, float eps,
+                           const float* g1, const void* dy1, int64_t ld_dy1,
+                           const float* g2, const void* dy2, int64_t ld_dy2, int32_t dy_dtype,
+                           const float* add, int64_t ld_add,
+                           float* dx, int64_t ld_dx, int32_t accumulate,
+                           void* dx_lp, int64_t ld_dx_lp, int32_t lp_dtype,
+                           float* dg1, float* db1, float* dg2, float* db2, void* stream);
+
+/* Backward of distb200_cross_attention (probabilities recomputed): dq [batch, heads*64], dkv [batch, keys, 2*heads*64]. */
+int distb200_cross_attention_bwd(const void* q, const void* kv, const void* d_out, void* dq, void* dkv, int32_t batch,
+                                 int32_t keys, int32_t heads, int32_t dtype, void* stream);
+
+/* Train-mode head + SoftTargetCrossEntropy (base_blocks.py:579-585 without softmax, losses.py:20-31) and its gradient:
+ * logits = scale * emb/|emb| . text_n^T;  loss[0] += mean_b sum_c -target * log_softmax(logits);
+ * d_emb = d loss / d emb.  logits may be NULL. */
+int distb200_softce_head(const float* emb, const float* text_n, float scale, const float* target, int32_t batch,
+                         int32_t embed_dim, int32_t classes, float* logits, float* loss, float* d_emb, void* stream);
+
+/* torch.optim.AdamW on n contiguous fp32 elements (decoupled decay, bias correction with `step` >= 1); the gradient
+ * is multiplied by grad_scale first (1 / world_size after a SUM all-reduce). */
+int distb200_adamw(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+                   float weight_decay, int32_t step, float grad_scale, void* stream);
+
+/* Operand copies of a master weight w [batch][n][k] fp32: out[b][n][k] (row pitch ld_out, columns [k, ld_out) zeroed)
+ * and out_t[b][k][n] (row pitch ld_out_t) in `dtype`; either may be NULL. */
+int distb200_pack_weight(const float* w, int64_t batch, int32_t n, int32_t k, void* out, int64_t ld_out, void* out_t,
+                         int64_t ld_out_t, int32_t dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

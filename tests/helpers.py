@@ -22,27 +22,39 @@ def check_inputs(fix, sd, clips, text, rtol=1e-6):
     assert close(synth.checksum(text), fix["text_checksum"]), "synthetic label embeddings differ from the fixture's"
 
 
+def gather_rows(a4, a_dim, tap, groups, rpg, img_w=0, group_dim=2):
+    """Rows A_j(gi, r, :) of the operand addressing in include/distb200.h for one tap (zero outside the tensor), fp64."""
+    dev = a4.device
+    gi = torch.arange(groups, device=dev).repeat_interleave(rpg)
+    r = torch.arange(rpg, device=dev).repeat(groups)
+    d1, d2, d3 = tap
+    if img_w > 0:
+        c1, c2, c3 = r % img_w + d1, r // img_w + d2, gi + d3
+    else:
+        c1 = r + d1
+        c2 = d2 + (gi if group_dim == 2 else 0)
+        c3 = d3 + (gi if group_dim == 3 else 0)
+        c2 = c2 if torch.is_tensor(c2) else torch.full_like(r, c2)
+        c3 = c3 if torch.is_tensor(c3) else torch.full_like(r, c3)
+    ok = (c1 >= 0) & (c1 < a_dim[1]) & (c2 >= 0) & (c2 < a_dim[2]) & (c3 >= 0) & (c3 < a_dim[3])
+    rows = a4[c3.clamp(0, a_dim[3] - 1), c2.clamp(0, a_dim[2] - 1), c1.clamp(0, a_dim[1] - 1)].double()
+    return rows * ok[:, None]
+
+
 def gemm_reference(a4, a_dim, taps, b3, groups, rpg, img_w=0, group_dim=2):
     """fp64 restatement of the operand addressing in include/distb200.h.
 
     a4: logical A tensor indexed [c3, c2, c1, k] (a torch tensor of shape a_dim reversed);
     b3: [taps, n, k].  Returns acc [groups*rpg, n]."""
     K = a_dim[0]
-    dev = a4.device
-    gi = torch.arange(groups, device=dev).repeat_interleave(rpg)
-    r = torch.arange(rpg, device=dev).repeat(groups)
-    acc = torch.zeros(groups * rpg, b3.shape[1], dtype=torch.float64, device=dev)
-    for j, (d1, d2, d3) in enumerate(taps):
-        if img_w > 0:
-            c1, c2, c3 = r % img_w + d1, r // img_w + d2, gi + d3
-        else:
-            c1 = r + d1
-            c2 = d2 + (gi if group_dim == 2 else 0)
-            c3 = d3 + (gi if group_dim == 3 else 0)
-            c2 = c2 if torch.is_tensor(c2) else torch.full_like(r, c2)
-            c3 = c3 if torch.is_tensor(c3) else torch.full_like(r, c3)
-        ok = (c1 >= 0) & (c1 < a_dim[1]) & (c2 >= 0) & (c2 < a_dim[2]) & (c3 >= 0) & (c3 < a_dim[3])
-        rows = a4[c3.clamp(0, a_dim[3] - 1), c2.clamp(0, a_dim[2] - 1), c1.clamp(0, a_dim[1] - 1)].double()
-        rows = rows * ok[:, None]
+    acc = torch.zeros(groups * rpg, b3.shape[1], dtype=torch.float64, device=a4.device)
+    for j, tap in enumerate(taps):
+        rows = gather_rows(a4, a_dim, tap, groups, rpg, img_w, group_dim)
         acc += rows[:, :K] @ b3[j].double()[:, :K].t()
     return acc
+
+
+def wgrad_reference(a4, a_dim, taps, dy, groups, rpg, img_w=0, group_dim=2):
+    """dw[j, n, k] = sum_rows dy[row, n] * A_j(row, k) in fp64; dy [groups*rpg, n] in output-row order."""
+    K = a_dim[0]
+    return torch.stack([dy.double().t() @ gather_rows(a4, a_dim, tap, groups, rpg, img_w, group_dim)[:, :K] for tap in taps])
