@@ -204,14 +204,13 @@ class DistEngine:
     def _ln(self, x, gb, y, **kw):
         self.calls.append(ops.layernorm(x, gb[0], gb[1], y, **kw))
 
-    def _plan(self):
+    def _plan_inputs(self):
+        """Patch rows, ViT embedding and temporal stem (everything that reads the clip)."""
         a, b, w = self.arch, self.batch, self.w
-        t, T, N, P, D, g = a.sparse_frames, a.frames, a.tokens, a.patches, a.width, a.grid
-        F, Ci, Ct, al = b * t, a.integration_dim, a.temporal_dim, a.alpha
-        Mv, Mt = F * N, b * T * P
+        t, T, N, P, D = a.sparse_frames, a.frames, a.tokens, a.patches, a.width
+        F, Ct, al = b * t, a.temporal_dim, a.alpha
         R = a.resolution
         add = self.calls.append
-        bf = self.precision == "bf16"
 
         # ---- patch rows: sparse frames for the ViT (clip.py:271 restricted to the frames kept at :281-284),
         #      all frames for the temporal stem (dist.py:225)
@@ -230,34 +229,55 @@ class DistEngine:
         self._ln(self.h, w.ln_pre, self.h, name="vit.ln_pre")
 
         # ---- temporal stem: Conv3d(3->Ct,(kt,ps,ps)) = kt row-shifted GEMMs over patch rows (dist.py:178-181,225)
+        self._plan_stem()
+
+    def _stem_operand(self):
+        """(a_dim, a_stride, taps) of the stem's A operand: the dense patch rows of a clip, kt row-shifted taps."""
+        a, b, w = self.arch, self.batch, self.w
+        T, P = a.frames, a.patches
         ks = 3 * a.s_patch * a.s_patch
         half = a.t_patch // 2
-        self._gemm(self.patches_d, w.stem_w, Ct, ks, a_dim=(ks, T * P, b, 1), a_stride=(1, w.kps, T * P * w.kps, b * T * P * w.kps),
-                   taps=[((k - half) * P, 0, 0) for k in range(a.t_patch)], b_tap_stride=Ct * w.kps, ldb=w.kps,
-                   groups=b, rows_per_group=T * P, bias=w.stem_b, out=self.xT, ld_out=Ct, name="dist.stem")
+        return ((ks, T * P, b, 1), (1, w.kps, T * P * w.kps, b * T * P * w.kps), [((k - half) * P, 0, 0) for k in range(a.t_patch)])
+
+    def _plan_stem(self):
+        a, b, w = self.arch, self.batch, self.w
+        Ct, ks = a.temporal_dim, 3 * a.s_patch * a.s_patch
+        a_dim, a_stride, taps = self._stem_operand()
+        self._gemm(self.patches_d, w.stem_w, Ct, ks, a_dim=a_dim, a_stride=a_stride, taps=taps, b_tap_stride=Ct * w.kps, ldb=w.kps,
+                   groups=b, rows_per_group=a.frames * a.patches, bias=w.stem_b, out=self.xT, ld_out=Ct, name="dist.stem")
+
+    def _plan(self):
+        a, b, w = self.arch, self.batch, self.w
+        t, N, D = a.sparse_frames, a.tokens, a.width
+        add = self.calls.append
+        bf = self.precision == "bf16"
+        self._plan_inputs()
 
         sel = list(a.selected_layers)
         monotonic = all(x < y for x, y in zip(sel, sel[1:]))
         assert monotonic, "SELECTED_LAYERS must be increasing (taps are consumed as the ViT produces them)"
         last_sel = sel[-1]
         for l in range(a.layers):
-            v = w.vit[l]
             want_tap = l in sel
-            # ---- ResidualAttentionBlockMid (clip.py:170-178) ----
-            self._ln(self.h, v["ln1"], self.ln_buf, name="vit.ln_1")
-            self._lin(self.ln_buf, v["qkv_w"], v["qkv_b"], self.qkv, name="vit.qkv")
-            add(ops.attention(self.qkv, self.attn_out, F, N, a.heads, impl=self.attn_impl, name="vit.attention"))
-            self._lin(self.attn_out, v["proj_w"], v["proj_b"], self.h, res=self.h, name="vit.out_proj")
-            self._ln(self.h, v["ln2"], self.ln_buf, name="vit.ln_2")
-            self._lin(self.ln_buf, v["fc1_w"], v["fc1_b"], self.fc1, act=ops.ACT_QUICKGELU, name="vit.fc1")
-            self._lin(self.fc1, v["fc2_w"], v["fc2_b"], self.h, res=self.h,
-                      out2=self.tap if (want_tap and bf) else None, name="vit.fc2")
+            self._plan_vit_layer(l, self.tap if (want_tap and bf) else None)
             if want_tap:
                 self._plan_dist_layer(sel.index(l))
             if l == last_sel:
                 # mean over the sparse frames of the last tapped class token (dist.py:243)
                 add(ops.mean_rows(self.h, N * D, t, b, D, self.clsmean, name="dist.cls_mean"))
         self._plan_head()
+
+    def _plan_vit_layer(self, l, tap_out):
+        """ResidualAttentionBlockMid (clip.py:170-178); ``tap_out`` receives a copy of the block output (the tap)."""
+        a, v = self.arch, self.w.vit[l]
+        F, N = self.batch * a.sparse_frames, a.tokens
+        self._ln(self.h, v["ln1"], self.ln_buf, name="vit.ln_1")
+        self._lin(self.ln_buf, v["qkv_w"], v["qkv_b"], self.qkv, name="vit.qkv")
+        self.calls.append(ops.attention(self.qkv, self.attn_out, F, N, a.heads, impl=self.attn_impl, name="vit.attention"))
+        self._lin(self.attn_out, v["proj_w"], v["proj_b"], self.h, res=self.h, name="vit.out_proj")
+        self._ln(self.h, v["ln2"], self.ln_buf, name="vit.ln_2")
+        self._lin(self.ln_buf, v["fc1_w"], v["fc1_b"], self.fc1, act=ops.ACT_QUICKGELU, name="vit.fc1")
+        self._lin(self.fc1, v["fc2_w"], v["fc2_b"], self.h, res=self.h, out2=tap_out, name="vit.fc2")
 
     def _plan_dist_layer(self, i):
         a, b, w = self.arch, self.batch, self.w
