@@ -93,44 +93,66 @@ __global__ void __launch_bounds__(256) group_sum_kernel(const void* src, int src
 // (block, column, period slot).  period > 1 (per-frame class tokens, positional embeddings) uses rows_per_group == 1.
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) colsum_kernel(const void* src, int dtype, long long ld, long long groups, long long rows_per_group,
-                                                     long long gstride, long long roff, long long period, int cols, float* out,
+                                                     long long gstride, long long roff, long long period, int cols, float* out, float* out2,
                                                      long long rows_per_block) {
-    __shared__ float red[8][33];
+    // thread = 4 consecutive columns (16-byte / 8-byte loads), 32 column vectors x 8 row lanes per block
+    __shared__ float4 red[8][33];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const int c = blockIdx.x * 32 + tx;
-    const long long total = groups * rows_per_group;
-    const long long r_begin = (long long)blockIdx.y * rows_per_block;
-    long long r_end = r_begin + rows_per_block;
-    if (r_end > total) r_end = total;
+    const int c = (blockIdx.x * 32 + tx) * 4;
+    const bool col_ok = c < cols;
     if (period == 1) {
-        float s = 0.f;
-        if (c < cols)
-            for (long long i = r_begin + ty; i < r_end; i += 8) {
-                const long long g = i / rows_per_group, r = i - g * rows_per_group;
-                s += ld_any(src, dtype, (g * gstride + roff + r) * ld + c);
+        const unsigned total = (unsigned)(groups * rows_per_group), rpg = (unsigned)rows_per_group;
+        const unsigned r_begin = (unsigned)(blockIdx.y * rows_per_block);
+        unsigned r_end = r_begin + (unsigned)rows_per_block;
+        if (r_end > total) r_end = total;
+        const bool dense = gstride == rows_per_group;          // rows of all groups are contiguous (plus roff)
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (col_ok) {
+            unsigned i = r_begin + ty;
+            for (; i + 24 < r_end; i += 32) {                   // four independent loads in flight
+                float4 v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const unsigned row = i + 8 * u;
+                    const long long srow = dense ? (long long)row + roff : (long long)(row / rpg) * gstride + roff + row % rpg;
+                    v[u] = ld4_any(src, dtype, srow * ld + c);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) { s.x += v[u].x; s.y += v[u].y; s.z += v[u].z; s.w += v[u].w; }
             }
+            for (; i < r_end; i += 8) {
+                const long long srow = dense ? (long long)i + roff : (long long)(i / rpg) * gstride + roff + i % rpg;
+                const float4 v = ld4_any(src, dtype, srow * ld + c);
+                s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+            }
+        }
         red[ty][tx] = s;
         __syncthreads();
-        if (ty == 0 && c < cols) {
-            float t = 0.f;
+        if (ty == 0 && col_ok) {
+            float4 t = red[0][tx];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) t += red[j][tx];
-            atomicAdd(out + c, t);
+            for (int j = 1; j < 8; ++j) { t.x += red[j][tx].x; t.y += red[j][tx].y; t.z += red[j][tx].z; t.w += red[j][tx].w; }
+            atomicAdd(out + c, t.x); atomicAdd(out + c + 1, t.y); atomicAdd(out + c + 2, t.z); atomicAdd(out + c + 3, t.w);
+            if (out2) { atomicAdd(out2 + c, t.x); atomicAdd(out2 + c + 1, t.y); atomicAdd(out2 + c + 2, t.z); atomicAdd(out2 + c + 3, t.w); }
         }
     } else {
         // slot p collects the groups g with g % period == p (rows_per_group rows each); blockIdx.y strides over p
         for (long long p = blockIdx.y; p < period; p += gridDim.y) {
-            float s = 0.f;
-            if (c < cols)
+            float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (col_ok)
                 for (long long g = p + (long long)ty * period; g < groups; g += 8 * period)
-                    for (long long r = 0; r < rows_per_group; ++r) s += ld_any(src, dtype, (g * gstride + roff + r) * ld + c);
+                    for (long long r = 0; r < rows_per_group; ++r) {
+                        const float4 v = ld4_any(src, dtype, (g * gstride + roff + r) * ld + c);
+                        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+                    }
             red[ty][tx] = s;
             __syncthreads();
-            if (ty == 0 && c < cols) {
-                float t = 0.f;
+            if (ty == 0 && col_ok) {
+                float4 t = red[0][tx];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) t += red[j][tx];
-                atomicAdd(out + p * cols + c, t);
+                for (int j = 1; j < 8; ++j) { t.x += red[j][tx].x; t.y += red[j][tx].y; t.z += red[j][tx].z; t.w += red[j][tx].w; }
+                float* o = out + p * cols + c;
+                atomicAdd(o, t.x); atomicAdd(o + 1, t.y); atomicAdd(o + 2, t.z); atomicAdd(o + 3, t.w);
             }
             __syncthreads();
         }
@@ -142,9 +164,10 @@ __global__ void __launch_bounds__(256) colsum_kernel(const void* src, int dtype,
 // gradients are reduced per block in shared memory (fp32 atomics within the block, then one global atomic per
 // column and block).
 // ---------------------------------------------------------------------------------------------------
-constexpr int LNB_MAXV = 8;
+constexpr int LNB_MAXV = 8;      // widest row: 128 * LNB_MAXV columns
 constexpr int LNB_WARPS = 8;
 
+template <int LNB_V>
 __global__ void __launch_bounds__(LNB_WARPS * 32) layernorm_bwd_kernel(
     const float* __restrict__ in1, long long ld_in1, const float* __restrict__ in2, long long ld_in2, long long in2_period, long long rows, int cols,
     float eps, const float* __restrict__ g1, const void* dy1, long long ld_dy1, const float* __restrict__ g2, const void* dy2, long long ld_dy2,
@@ -154,9 +177,9 @@ __global__ void __launch_bounds__(LNB_WARPS * 32) layernorm_bwd_kernel(
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < 4 * cols; i += blockDim.x) sh[i] = 0.f;
     __syncthreads();
-    float a_dg1[LNB_MAXV][4], a_db1[LNB_MAXV][4], a_dg2[LNB_MAXV][4], a_db2[LNB_MAXV][4];
+    float a_dg1[LNB_V][4], a_db1[LNB_V][4], a_dg2[LNB_V][4], a_db2[LNB_V][4];
 #pragma unroll
-    for (int i = 0; i < LNB_MAXV; ++i)
+    for (int i = 0; i < LNB_V; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) a_dg1[i][j] = a_db1[i][j] = a_dg2[i][j] = a_db2[i][j] = 0.f;
 
@@ -166,10 +189,10 @@ __global__ void __launch_bounds__(LNB_WARPS * 32) layernorm_bwd_kernel(
         if (row >= rows) break;
         const float* x = in1 + row * ld_in1;
         const float* x2 = in2 ? in2 + (row % in2_period) * ld_in2 : nullptr;
-        float4 v[LNB_MAXV];
+        float4 v[LNB_V];
         float sum = 0.f;
 #pragma unroll
-        for (int i = 0; i < LNB_MAXV; ++i) {
+        for (int i = 0; i < LNB_V; ++i) {
             const int c = (i * 32 + lane) * 4;
             if (c < cols) {
                 v[i] = *reinterpret_cast<const float4*>(x + c);
@@ -183,7 +206,7 @@ __global__ void __launch_bounds__(LNB_WARPS * 32) layernorm_bwd_kernel(
         const float mean = warp_sum(sum) / (float)cols;
         float sq = 0.f;
 #pragma unroll
-        for (int i = 0; i < LNB_MAXV; ++i) {
+        for (int i = 0; i < LNB_V; ++i) {
             const int c = (i * 32 + lane) * 4;
             if (c < cols) {
                 v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
@@ -192,10 +215,10 @@ __global__ void __launch_bounds__(LNB_WARPS * 32) layernorm_bwd_kernel(
         }
         const float rstd = rsqrtf(warp_sum(sq) / (float)cols + eps);
         // g = dy1*g1 + dy2*g2; accumulate parameter gradients; row means of g and g*xhat
-        float4 g[LNB_MAXV];
+        float4 g[LNB_V];
         float sg = 0.f, sgx = 0.f;
 #pragma unroll
-        for (int i = 0; i < LNB_MAXV; ++i) {
+        for (int i = 0; i < LNB_V; ++i) {
             const int c = (i * 32 + lane) * 4;
             if (c < cols) {
                 v[i].x *= rstd; v[i].y *= rstd; v[i].z *= rstd; v[i].w *= rstd;          // xhat
@@ -217,7 +240,7 @@ __global__ void __launch_bounds__(LNB_WARPS * 32) layernorm_bwd_kernel(
         }
         const float mg = warp_sum(sg) / (float)cols, mgx = warp_sum(sgx) / (float)cols;
 #pragma unroll
-        for (int i = 0; i < LNB_MAXV; ++i) {
+        for (int i = 0; i < LNB_V; ++i) {
             const int c = (i * 32 + lane) * 4;
             if (c < cols) {
                 float4 o = make_float4(rstd * (g[i].x - mg - v[i].x * mgx), rstd * (g[i].y - mg - v[i].y * mgx),
@@ -240,7 +263,7 @@ __global__ void __launch_bounds__(LNB_WARPS * 32) layernorm_bwd_kernel(
     }
     // block reduction of the parameter gradients
 #pragma unroll
-    for (int i = 0; i < LNB_MAXV; ++i) {
+    for (int i = 0; i < LNB_V; ++i) {
         const int c = (i * 32 + lane) * 4;
         if (c < cols) {
 #pragma unroll
@@ -487,22 +510,26 @@ extern "C" int distb200_group_sum(const void* src, int32_t src_dtype, int64_t gr
 }
 
 extern "C" int distb200_colsum(const void* src, int32_t src_dtype, int64_t ld, int64_t groups, int64_t rows_per_group, int64_t gstride,
-                               int64_t roff, int64_t period, int32_t cols, float* out, void* stream) {
+                               int64_t roff, int64_t period, int32_t cols, float* out, float* out2, void* stream) {
     if (groups == 0 || rows_per_group == 0 || cols == 0) return 0;
     DISTB200_REQUIRE(src && out && period >= 1 && DISTB200_DTYPE_OK(src_dtype), "colsum: bad arguments");
+    DISTB200_REQUIRE(cols % 4 == 0 && ld % 4 == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0, "colsum: cols and ld must be multiples of 4, src 16-byte aligned");
+    DISTB200_REQUIRE(!out2 || period == 1, "colsum: the second output needs period == 1");
     const long long total = groups * rows_per_group;
-    dim3 grid((unsigned)((cols + 31) / 32), 1);
+    DISTB200_REQUIRE(total < (1ll << 31), "colsum: too many rows");
+    dim3 grid((unsigned)((cols / 4 + 31) / 32), 1);
     long long rows_per_block = total;
     if (period == 1) {
-        long long splits = (long long)sm_count() * 4 / grid.x;
+        long long splits = (long long)sm_count() * 8 / grid.x;
         if (splits < 1) splits = 1;
         rows_per_block = (total + splits - 1) / splits;
-        if (rows_per_block < 64) rows_per_block = 64;
+        if (rows_per_block < 128) rows_per_block = 128;
         grid.y = (unsigned)((total + rows_per_block - 1) / rows_per_block);
     } else {
         grid.y = (unsigned)(period < 65535 ? period : 65535);
     }
-    colsum_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, src_dtype, ld, groups, rows_per_group, gstride, roff, period, cols, out, rows_per_block);
+    colsum_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, src_dtype, ld, groups, rows_per_group, gstride, roff, period, cols, out, out2,
+                                                          rows_per_block);
     return check_launch("colsum");
 }
 
@@ -527,9 +554,18 @@ extern "C" int distb200_layernorm_bwd(const float* in1, int64_t ld_in1, const fl
     if (rows_per_warp < 1) rows_per_warp = 1;
     const long long blocks = (rows + (long long)LNB_WARPS * rows_per_warp - 1) / ((long long)LNB_WARPS * rows_per_warp);
     const size_t smem = (size_t)4 * cols * sizeof(float);
-    layernorm_bwd_kernel<<<(unsigned)blocks, LNB_WARPS * 32, smem, (cudaStream_t)stream>>>(
-        in1, ld_in1, in2, ld_in2, in2_period, rows, cols, eps, g1, dy1, ld_dy1, g2, dy2, ld_dy2, dy_dtype, add, ld_add, dx, ld_dx, accumulate, dx_lp,
-        ld_dx_lp, lp_dtype, dg1, db1, dg2, db2, rows_per_warp);
+#define DISTB200_LNB(V)                                                                                                                  \
+    layernorm_bwd_kernel<V><<<(unsigned)blocks, LNB_WARPS * 32, smem, (cudaStream_t)stream>>>(                                          \
+        in1, ld_in1, in2, ld_in2, in2_period, rows, cols, eps, g1, dy1, ld_dy1, g2, dy2, ld_dy2, dy_dtype, add, ld_add, dx, ld_dx, accumulate, dx_lp, \
+        ld_dx_lp, lp_dtype, dg1, db1, dg2, db2, rows_per_warp)
+    // float4 per lane: the register footprint (and with it the number of resident warps) follows the row width
+    if (cols <= 128) DISTB200_LNB(1);
+    else if (cols <= 256) DISTB200_LNB(2);
+    else if (cols <= 384) DISTB200_LNB(3);
+    else if (cols <= 512) DISTB200_LNB(4);
+    else if (cols <= 768) DISTB200_LNB(6);
+    else DISTB200_LNB(8);
+#undef DISTB200_LNB
     return check_launch("layernorm_bwd");
 }
 

@@ -96,7 +96,7 @@ def lib():
     L.distb200_quickgelu_bwd.argtypes = [vp, i32, vp, i32, vp, vp, i32, i64, vp]
     L.distb200_cast.argtypes = [vp, vp, i32, i64, vp]
     L.distb200_group_sum.argtypes = [vp, i32, i64, i32, i64, vp, i32, vp]
-    L.distb200_colsum.argtypes = [vp, i32, i64, i64, i64, i64, i64, i64, i32, vp, vp]
+    L.distb200_colsum.argtypes = [vp, i32, i64, i64, i64, i64, i64, i64, i32, vp, vp, vp]
     L.distb200_layernorm_bwd.argtypes = [vp, i64, vp, i64, i64, i64, i32, f32, vp, vp, i64, vp, vp, i64, i32, vp, i64, vp, i64, i32,
                                          vp, i64, i32, vp, vp, vp, vp, vp]
     L.distb200_cross_attention_bwd.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]
@@ -324,14 +324,15 @@ def group_sum(src, dst, groups, alpha, inner, name="group_sum"):
     return Call(lib().distb200_group_sum, args, name, keep=(src, dst), nbytes=groups * inner * (alpha * src.element_size() + dst.element_size()))
 
 
-def colsum(src, out, cols, *, ld=None, groups=1, rows_per_group=None, gstride=None, roff=0, period=1, name="colsum"):
+def colsum(src, out, cols, *, ld=None, groups=1, rows_per_group=None, gstride=None, roff=0, period=1, out2=None, name="colsum"):
     assert out.dtype == torch.float32
     ld = int(ld if ld is not None else cols)
     if rows_per_group is None:
         rows_per_group = src.numel() // ld
     gstride = int(gstride if gstride is not None else rows_per_group)
-    args = (src.data_ptr(), enum_of(src), ld, int(groups), int(rows_per_group), gstride, int(roff), int(period), int(cols), out.data_ptr())
-    return Call(lib().distb200_colsum, args, name, keep=(src, out), nbytes=int(groups) * int(rows_per_group) * int(cols) * src.element_size())
+    args = (src.data_ptr(), enum_of(src), ld, int(groups), int(rows_per_group), gstride, int(roff), int(period), int(cols), out.data_ptr(),
+            _ptr(out2))
+    return Call(lib().distb200_colsum, args, name, keep=(src, out, out2), nbytes=int(groups) * int(rows_per_group) * int(cols) * src.element_size())
 
 
 def layernorm_bwd(x, g1, dy1, *, rows=None, cols=None, in2=None, in2_period=1, g2=None, dy2=None, add=None, dx=None, accumulate=False,

@@ -221,15 +221,16 @@ class TrainEngine(DistEngine):
         self._gemm(x, m.f[tap], m.n, m.k, ldb=m.kp, bias=None if bias is None else bias.p, res=res, ld_res=m.n, out=out,
                    ld_out=kw.pop("ld_out", m.n), out2=out2, ld_out2=m.n, name=name, **kw)
 
-    def _bwd_lin(self, dy_lp, x_lp, m: Mat, bias, dy_f32=None, *, dx=None, dx_res=None, dx2=None, ld_x=None, ld_dy=None, name="linear"):
+    def _bwd_lin(self, dy_lp, x_lp, m: Mat, bias, dy_f32=None, *, bias2=None, dx=None, dx_res=None, dx2=None, ld_x=None, ld_dy=None, name="linear"):
         """weight / bias gradients of a plain linear and (optionally) dx = dy @ W (+ dx_res), rows = dy rows"""
         B = self.bwd.append
         rows = dy_lp.shape[0]
         B(ops.wgrad(x_lp, dy_lp, m.g[0], m.n, m.k, a_dim=(m.k, rows, 1, 1), a_stride=(1, ld_x or x_lp.stride(0), 0, 0), rows_per_group=rows,
                     ld_dy=ld_dy or dy_lp.stride(0), ld_dw=m.k, impl=self.gemm_impl, name="bwd." + name + ".wgrad"))
         if bias is not None:
-            src = dy_f32 if dy_f32 is not None else dy_lp
-            B(ops.colsum(src, bias.g, m.n, ld=src.stride(0), rows_per_group=rows, name="bwd." + name + ".bgrad"))
+            # the low-precision copy is read (half the bytes of the fp32 gradient; the sum itself is fp32)
+            B(ops.colsum(dy_lp, bias.g, m.n, ld=ld_dy or dy_lp.stride(0), rows_per_group=rows, out2=None if bias2 is None else bias2.g,
+                         name="bwd." + name + ".bgrad"))
         if dx is not None or dx2 is not None:
             if dx is None:
                 dx, dx2 = dx2, None
@@ -325,14 +326,16 @@ class TrainEngine(DistEngine):
         # =========================== backward ===========================
         self._plan_head_bwd()                           # leaves d loss / d cur in self.GA
         GR, GU = self.GA, self.GB
+        GR_a, GU_a = self.GR_a, self.GU_a
         for i in reversed(range(nl)):
             s, p = S[i], P_[i]
             last = i == nl - 1
             nm = "dist%d." % i
-            B(ops.cast(GR, self.GR_a, name="bwd." + nm + "cast_gres"))
-            # ---- projections of the IntegrationNetwork: res = hf W_p^T + b_p + ht W_tp^T + b_tp
-            self._bwd_lin(self.GR_a, s["hf"], p["wpr"], p["bpr"], GR, dx2=self.g_hf, name=nm + "int.ffn_proj")
-            self._bwd_lin(self.GR_a, s["ht"], p["wtpr"], p["btpr"], GR, dx2=self.g_ht, name=nm + "int.t_proj")
+            if last:
+                B(ops.cast(GR, GR_a, name="bwd." + nm + "cast_gres"))      # later layers inherit the copy written with GU
+            # ---- projections of the IntegrationNetwork: res = hf W_p^T + b_p + ht W_tp^T + b_tp (both biases see the same sum)
+            self._bwd_lin(GR_a, s["hf"], p["wpr"], p["bpr"], bias2=p["btpr"], dx2=self.g_hf, name=nm + "int.ffn_proj")
+            self._bwd_lin(GR_a, s["ht"], p["wtpr"], None, dx2=self.g_ht, name=nm + "int.t_proj")
             B(ops.quickgelu_bwd(self.g_hf, s["zf"], None, self.g_zf, name="bwd." + nm + "int.act_f"))
             B(ops.quickgelu_bwd(self.g_ht, s["zt"], None, self.g_zt, name="bwd." + nm + "int.act_t"))
             self._bwd_lin(self.g_zf, s["a1"], p["wfc"], p["bfc"], dx2=self.g_a1, name=nm + "int.ffn_fc")
@@ -346,19 +349,19 @@ class TrainEngine(DistEngine):
             self._bwd_lin(self.g_tf1, s["a2"], p["wtf1"], p["btf1"], dx2=self.g_a2, name=nm + "int.t_fc1")
             # ---- LayerNorm pair -> gradient of upd (plus the direct path cur = res + upd of the last layer)
             B(ops.layernorm_bwd(s["upd"], p["ln"][0].p, self.g_a1, g2=p["ln_t"][0].p, dy2=self.g_a2, add=GR if last else None, dx=GU,
-                                dx_lp=self.GU_a, dg1=p["ln"][0].g, db1=p["ln"][1].g, dg2=p["ln_t"][0].g, db2=p["ln_t"][1].g,
+                                dx_lp=GU_a, dg1=p["ln"][0].g, db1=p["ln"][1].g, dg2=p["ln_t"][0].g, db2=p["ln_t"][1].g,
                                 name="bwd." + nm + "int.ln"))
             B(ops.colsum(GU, p["cls"].g, Ci, groups=F, rows_per_group=1, gstride=N, roff=0, period=t, name="bwd." + nm + "t2i.cls"))
             # ---- integration -> temporal, part 1: collect the alpha dense frames of every sparse frame (needs the untouched GX)
             if not last:
                 B(ops.group_sum(self.GX, self.d_u, F, al, P * Ct, name="bwd." + nm + "i2t.frame_sum"))
             # ---- temporal -> integration: d_v = GU[:, 1:]
-            B(ops.wgrad(s["xT_a"], self.GU_a, p["wt2i"].g, Ci, Ct, a_dim=(Ct, P, al, F), a_stride=(1, Ct, P * Ct, al * P * Ct), group_dim=3,
+            B(ops.wgrad(s["xT_a"], GU_a, p["wt2i"].g, Ci, Ct, a_dim=(Ct, P, al, F), a_stride=(1, Ct, P * Ct, al * P * Ct), group_dim=3,
                         taps=[(0, k, 0) for k in range(al)], groups=F, rows_per_group=P, dy_gstride=N, dy_roff=1, impl=self.gemm_impl,
                         name="bwd." + nm + "t2i.wgrad"))
-            B(ops.colsum(GU, p["bt2i"].g, Ci, groups=F, rows_per_group=P, gstride=N, roff=1, name="bwd." + nm + "t2i.bgrad"))
+            B(ops.colsum(GU_a, p["bt2i"].g, Ci, groups=F, rows_per_group=P, gstride=N, roff=1, name="bwd." + nm + "t2i.bgrad"))
             for k in range(al):
-                self._bgemm(self.GU_a, p["wt2i"].t[k], Ct, Ci, a_dim=(Ci, N, F, 1), a_stride=(1, Ci, N * Ci, Mv * Ci), taps=[(1, 0, 0)], groups=F,
+                self._bgemm(GU_a, p["wt2i"].t[k], Ct, Ci, a_dim=(Ci, N, F, 1), a_stride=(1, Ci, N * Ci, Mv * Ci), taps=[(1, 0, 0)], groups=F,
                             rows_per_group=P, ldb=p["wt2i"].np_, res=None if last else self.GX, ld_res=Ct, res_gstride=al * P, res_roff=k * P,
                             out=self.GX, ld_out=Ct, out_gstride=al * P, out_roff=k * P, name="bwd." + nm + "t2i.dgrad%d" % k)
             # ---- integration -> temporal, part 2
@@ -368,14 +371,14 @@ class TrainEngine(DistEngine):
                 B(ops.colsum(self.d_u, p["bi2t"].g, Ct, name="bwd." + nm + "i2t.bgrad"))
                 self._bgemm(self.d_u, p["wi2t"].t[0], Ci, Ct, a_dim=(Ct, P, F, 1), a_stride=(1, Ct, P * Ct, F * P * Ct), groups=F, rows_per_group=P,
                             ldb=p["wi2t"].np_, res=GU, ld_res=Ci, res_gstride=N, res_roff=1, out=GU, ld_out=Ci, out_gstride=N, out_roff=1,
-                            out2=self.GU_a, ld_out2=Ci, name="bwd." + nm + "i2t.dgrad")
+                            out2=GU_a, ld_out2=Ci, name="bwd." + nm + "i2t.dgrad")
             # ---- input linear: only parameters (the taps come from the frozen ViT)
-            self._bwd_lin(self.GU_a, s["tap"], p["win"], p["bin"], GU, name=nm + "input_linear")
+            self._bwd_lin(GU_a, s["tap"], p["win"], p["bin"], name=nm + "input_linear")
             # ---- TemporalNet: GX = gradient of the post-activation stream
             B(ops.quickgelu_bwd(self.GX, s["z2"], self.GZ2, self.GZ2_a, name="bwd." + nm + "tn.act2"))
             B(ops.wgrad(s["y1"], self.GZ2_a, p["w2"].g, Ct, Ch, a_dim=(Ch, g, g, b * T), a_stride=(1, Ch, g * Ch, P * Ch), img_w=g, taps=conv_s_taps,
                         groups=b * T, rows_per_group=P, impl=self.gemm_impl, name="bwd." + nm + "tn.conv_s.wgrad"))
-            B(ops.colsum(self.GZ2, p["b2"].g, Ct, name="bwd." + nm + "tn.conv_s.bgrad"))
+            B(ops.colsum(self.GZ2_a, p["b2"].g, Ct, name="bwd." + nm + "tn.conv_s.bgrad"))
             self._bgemm(self.GZ2_a, p["w2"].t, Ch, Ct, a_dim=(Ct, g, g, b * T), a_stride=(1, Ct, g * Ct, P * Ct), img_w=g, taps=neg(conv_s_taps),
                         b_tap_stride=Ch * p["w2"].np_, ldb=p["w2"].np_, groups=b * T, rows_per_group=P, out=self.g_y1, ld_out=Ch,
                         name="bwd." + nm + "tn.conv_s.dgrad")
@@ -389,13 +392,14 @@ class TrainEngine(DistEngine):
             B(ops.layernorm_bwd(s["xT_in"], p["tn_ln"][0].p, self.g_xln, add=self.GZ2, dx=self.GX, dx_lp=self.GX_a if i == 0 else None,
                                 dg1=p["tn_ln"][0].g, db1=p["tn_ln"][1].g, name="bwd." + nm + "tn.ln"))
             GR, GU = GU, GR                               # the gradient of this layer's mid is the gradient of res_{i-1}
+            GR_a, GU_a = GU_a, GR_a
         # ---- temporal stem (parameters only)
         stem = pt.mat("dist_net.temporal_stem.weight")
         a_dim, a_stride, taps = self._stem_operand()
         ks = 3 * a.s_patch * a.s_patch
         B(ops.wgrad(self.patches_d, self.GX_a, stem.g, Ct, ks, a_dim=a_dim, a_stride=a_stride, taps=taps, groups=b, rows_per_group=T * P,
                     ld_dw=ks, impl=self.gemm_impl, name="bwd.stem.wgrad"))
-        B(ops.colsum(self.GX, V("dist_net.temporal_stem.bias").g, Ct, name="bwd.stem.bgrad"))
+        B(ops.colsum(self.GX_a, V("dist_net.temporal_stem.bias").g, Ct, name="bwd.stem.bgrad"))
 
         # =========================== operand refresh ===========================
         self.pack_calls = [m.pack_call(k) for k, m in sorted(pt.mats.items())]

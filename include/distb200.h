@@ -202,9 +202,10 @@ int distb200_group_sum(const void* src, int32_t src_dtype, int64_t groups, int32
                        int32_t dst_dtype, void* stream);
 
 /* out[(g % period)*cols + c] += sum_{r < rows_per_group} src[(g*gstride + roff + r)*ld + c]   (bias.grad, cls_token.grad,
- * positional_embedding.grad, aggregated token grads). */
+ * positional_embedding.grad, aggregated token grads).  out2, when non-NULL (period == 1 only), receives the same sums (two
+ * biases fed by the same gradient).  cols and ld must be multiples of 4. */
 int distb200_colsum(const void* src, int32_t src_dtype, int64_t ld, int64_t groups, int64_t rows_per_group, int64_t gstride,
-                    int64_t roff, int64_t period, int32_t cols, float* out, void* stream);
+                    int64_t roff, int64_t period, int32_t cols, float* out, float* out2, void* stream);
 
 /* Backward of distb200_layernorm for x = in1 (+ in2[row % in2_period]); statistics are recomputed from x.
  *   dx_row = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy1 * g1 (+ dy2 * g2)
