@@ -42,6 +42,7 @@ WORKLOADS = {
     "b16_8x16": dict(arch=dict(), cfg="configs/projects/dist/ssv2/vit-b16-8+16f.yaml", label="DiST ViT-B/16 8+16f SSV2"),
     "b16_32x64": dict(arch=dict(frames=64, ada_layers=4, num_classes=400), cfg="configs/projects/dist/k400/vit-b16-32+64f.yaml",
                       label="DiST ViT-B/16 32+64f K400"),
+    "b16_16x32": dict(arch=dict(frames=32), cfg="configs/projects/dist/ssv2/vit-b16-16+32f.yaml", label="DiST ViT-B/16 16+32f SSV2"),
     "l14_32x64": dict(arch=dict(width=1024, layers=24, patch=14, embed_dim=768, frames=64, s_patch=14, ada_layers=4,
                                 num_classes=400, selected_layers=list(range(24))),
                       cfg="configs/projects/dist/k400/vit-l14-32+64f.yaml", label="DiST ViT-L/14 32+64f K400"),
@@ -193,6 +194,86 @@ def family(call):
     return "gemm_vit" if n.startswith("vit.") else "gemm_dist"
 
 
+def run_train(args, arch, wl, world, rank, local, dev):
+    """Fine-tuning step (frozen CLIP forward, DiST forward + backward, flat NCCL gradient all-reduce, AdamW)."""
+    import torch.distributed as dist
+    from dist_b200.train import TrainEngine
+    sd = synth.synth_state_dict(arch, seed=0, init="reference")
+    text = synth.synth_text_features(arch.num_classes, arch.embed_dim)
+    b = args.clips
+    base = synth.synth_clips(min(b, 4), arch, seed=1234 + rank, kind="structured")
+    clips = base.repeat((b + base.shape[0] - 1) // base.shape[0], 1, 1, 1, 1)[:b].contiguous()
+    target = synth.synth_soft_targets(b, arch.num_classes, seed=99 + rank)
+    eng = TrainEngine(sd, arch, b, device=dev, precision=args.precision, text_features=text, weight_decay=1e-4)
+    eng.capture()
+    d_clips, d_target = clips.to(dev), target.to(dev)
+    lr = 3.2e-4                                        # BASE_LR 3.2e-5 x NEW_NET_LRMULT 10 (ssv2/vit-b16-16+32f.yaml:53-54)
+
+    def timed(fn, steps):
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        torch.cuda.synchronize()
+        wall = (time.perf_counter() - t0) * 1e3
+        if world > 1:
+            dist.barrier()
+        ms = torch.tensor([max(e0.elapsed_time(e1), 0.0), wall], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms[0]), float(ms[1])
+
+    for i in range(args.warmup):
+        eng.train_step(d_clips, d_target, lr)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    total_ms, _ = timed(lambda i: eng.train_step(d_clips, d_target, lr), args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * b * args.steps / (total_ms / 1e3)
+
+    # end to end: pinned host clips + soft targets in, loss out, every step
+    host = [clips.clone().pin_memory(), clips.flip(0).clone().pin_memory()]
+    host_t = target.clone().pin_memory()
+    loss_host = torch.empty(1).pin_memory()
+
+    def e2e_step(i):
+        loss = eng.train_step(host[i & 1], host_t, lr)
+        loss_host.copy_(loss, non_blocking=False)
+
+    for i in range(2):
+        e2e_step(i)
+    ems, ewall = timed(e2e_step, args.steps)
+    ems = max(ems, ewall)
+    if rank == 0:
+        pk = peaks()
+        fwd_fl, bwd_fl = sum(c.flops for c in eng.calls), sum(c.flops for c in eng.bwd)
+        line = {
+            "metric": "clips/sec", "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+            "config": {"workload": "%s fine-tuning step (frozen CLIP forward, DiST forward + backward, AdamW), %d synthetic clips per GPU, "
+                                   "flat NCCL all-reduce of %.2f M trainable gradients" % (wl["label"], b, eng.pt.n_used / 1e6),
+                       "clips_per_gpu": b, "precision": args.precision, "cuda_graph": "forward + backward", "optimizer": "AdamW lr 3.2e-4 wd 1e-4",
+                       "gflop_per_clip": round((fwd_fl + bwd_fl) / b / 1e9, 1)},
+            "model_tflops": value / world * (fwd_fl + bwd_fl) / b / 1e12,
+            "e2e": {"value": world * b * args.steps / (ems / 1e3), "unit": "clips/s", "h2d_bytes_per_step": int(clips.numel() * 4 + target.numel() * 4),
+                    "d2h_bytes_per_step": 4, "ms_per_step": ems / args.steps},
+            "gpu_launches": (len(eng.calls) + len(eng.bwd) + len(eng.pack_calls) + 2) * args.steps,
+            "launches_per_step": len(eng.calls) + len(eng.bwd) + len(eng.pack_calls) + 2, "loss": float(eng.loss), "clocks": clocks,
+            "peaks": {"bf16_tflops_sustained": pk["tf_sustained"], "hbm_gbs": pk["hbm"]},
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -204,6 +285,8 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--mode", default="infer", choices=["infer", "train"],
+                    help="train = one fine-tuning step per step (BASELINE configs[4]; use --workload b16_16x32)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
 
@@ -221,6 +304,10 @@ def main():
     import torch.distributed as dist
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+
+    if args.mode == "train":
+        run_train(args, arch, wl, world, rank, local, dev)
+        return
 
     from dist_b200.engine import DistEngine
     sd = synth.synth_state_dict(arch, seed=0, init="reference")

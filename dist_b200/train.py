@@ -149,6 +149,20 @@ class ParamTable:
         return {k: self.unpack[k](self._view(buf, k).detach().float().cpu()).contiguous() for k in self.names}
 
 
+def reduce_gradients(pt, group=None):
+    """SUM all-reduce of the used part of the flat gradient buffer (one collective for all ``dist_net`` tensors; the
+    reference's DDP reduces buckets over every parameter of the model, ``models/base/builder.py:69-74``).  Returns the
+    factor the update applies to the summed gradient (1 / world size = DDP's mean)."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return 1.0
+    world = dist.get_world_size(group)
+    if world == 1:
+        return 1.0
+    dist.all_reduce(pt.g[:pt.n_used], group=group)
+    return 1.0 / world
+
+
 # ---- the engine ----------------------------------------------------------------------------------------------------
 
 class TrainEngine(DistEngine):
@@ -581,12 +595,7 @@ class TrainEngine(DistEngine):
     def optimizer_step(self, lr):
         """Gradient averaging over the process group, AdamW on the two decay classes, operand refresh."""
         pt = self.pt
-        scale = 1.0
-        if self.process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
-            world = torch.distributed.get_world_size(self.process_group)
-            if world > 1:
-                torch.distributed.all_reduce(pt.g[:pt.n_used], group=self.process_group)      # SUM; averaged inside the update
-                scale = 1.0 / world
+        scale = reduce_gradients(pt, self.process_group)
         self.step_count += 1
         st = torch.cuda.current_stream(self.device).cuda_stream
         b1, b2 = self.betas
