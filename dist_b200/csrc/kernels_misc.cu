@@ -25,14 +25,14 @@ __device__ __forceinline__ void ln_store4<bf16>(bf16* y, int c, float4 v) {
 
 // LPR lanes cooperate on one row (32 for wide rows; 8 for rows of <= 128 floats such as the Ct = 96 temporal
 // stream, so that a warp covers 4 rows and no lane idles); each lane holds up to LN_MAXV float4 of its row.
-template <typename OutT, int LPR>
-__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ in1, long long ld_in1,
+template <typename OutT, int LPR, int V>
+__global__ void __launch_bounds__(256, V <= 6 ? 5 : 4) layernorm_kernel(const float* __restrict__ in1, long long ld_in1,
                                                         const float* __restrict__ in2, long long ld_in2, long long in2_period,
                                                         long long rows, int cols, float eps,
                                                         const float* __restrict__ g1, const float* __restrict__ b1, OutT* y1, long long ld_y1,
                                                         const float* __restrict__ g2, const float* __restrict__ b2, OutT* y2, long long ld_y2) {
     constexpr int RPW = 32 / LPR;                       // rows per warp
-    constexpr int MAXV = LPR == 32 ? LN_MAXV : 4;
+    constexpr int MAXV = V;                             // float4 per lane: cols <= 4 * LPR * V
     const int lane = threadIdx.x & 31, sub = lane % LPR;
     const long long row = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW + lane / LPR;
     const bool row_ok = row < rows;
@@ -119,6 +119,53 @@ __global__ void __launch_bounds__(256) patchify_kernel(const float* __restrict__
             else *reinterpret_cast<float2*>(px) = *reinterpret_cast<const float2*>(src + x);
             const int pc = x / p, ix = x - pc * p;
             store_pixels<OutT, VEC>(dst + (long long)pc * ld_out + ix, px);
+        }
+    }
+}
+
+
+// patchify straight from decoded frames: uint8 [clips, T, H, W, 3] (the decoder's layout, before ToTensorVideo) with the
+// normalisation (x / 255 - mean) / std fused in - same operation order as torchvision's to_tensor + normalize, so the fp32
+// result is bit-identical to patchifying the normalised float clip.  Thread = VEC pixels (3 * VEC contiguous bytes).
+template <typename OutT, int VEC, int TPR>
+__global__ void __launch_bounds__(256) patchify_u8_kernel(const uint8_t* __restrict__ frames, OutT* __restrict__ out, int clips, int T, int H, int W,
+                                                          int p, int first, int step, int n_sel, long long ld_out, float m0, float m1, float m2,
+                                                          float s0, float s1, float s2) {
+    constexpr int RPB = 256 / TPR;
+    const int g = W / p;
+    const long long n_rows = (long long)clips * n_sel * H;
+    const int tx = threadIdx.x % TPR;
+    const float mean[3] = {m0, m1, m2}, sd[3] = {s0, s1, s2};
+    for (long long row = (long long)blockIdx.x * RPB + threadIdx.x / TPR; row < n_rows; row += (long long)gridDim.x * RPB) {
+        long long rest = row;
+        const int y = (int)(rest % H); rest /= H;
+        const int i = (int)(rest % n_sel);
+        const int clip = (int)(rest / n_sel);
+        const int frame = first + i * step;
+        const uint8_t* src = frames + (((long long)clip * T + frame) * H + y) * W * 3;
+        const int pr = y / p, iy = y - pr * p;
+        OutT* dst = out + (((long long)clip * n_sel + i) * (g * g) + (long long)pr * g) * ld_out + iy * p;
+        for (int x = tx * VEC; x < W; x += TPR * VEC) {
+            uint8_t b[3 * VEC];
+            if (VEC == 4) {
+                const uint32_t* s32 = reinterpret_cast<const uint32_t*>(src + 3 * x);
+                uint32_t w3[3] = {s32[0], s32[1], s32[2]};
+#pragma unroll
+                for (int j = 0; j < 12; ++j) b[j] = (uint8_t)(w3[j >> 2] >> (8 * (j & 3)));
+            } else {
+                const uint16_t* s16 = reinterpret_cast<const uint16_t*>(src + 3 * x);
+                uint16_t w3[3] = {s16[0], s16[1], s16[2]};
+#pragma unroll
+                for (int j = 0; j < 6; ++j) b[j] = (uint8_t)(w3[j >> 1] >> (8 * (j & 1)));
+            }
+            const int pc = x / p, ix = x - pc * p;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                float px[VEC];
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) px[v] = ((float)b[3 * v + c] / 255.0f - mean[c]) / sd[c];
+                store_pixels<OutT, VEC>(dst + (long long)pc * ld_out + c * p * p + ix, px);
+            }
         }
     }
 }
@@ -314,14 +361,21 @@ extern "C" int distb200_layernorm(const float* in1, int64_t ld_in1, const float*
     DISTB200_REQUIRE(in2_period >= 1, "layernorm: in2_period must be >= 1");
     const int wpb = 8;
     cudaStream_t st = (cudaStream_t)stream;
-#define DISTB200_LN(T, LPR)                                                                                                         \
-    layernorm_kernel<T, LPR><<<(unsigned)((rows + wpb * (32 / LPR) - 1) / (wpb * (32 / LPR))), wpb * 32, 0, st>>>(                  \
+#define DISTB200_LN(T, LPR, V)                                                                                                      \
+    layernorm_kernel<T, LPR, V><<<(unsigned)((rows + wpb * (32 / LPR) - 1) / (wpb * (32 / LPR))), wpb * 32, 0, st>>>(               \
         in1, ld_in1, in2, ld_in2, in2_period, rows, cols, eps, g1, b1, (T*)y1, ld_y1, g2, b2, (T*)y2, ld_y2)
-    if (cols <= 128) {
-        if (out_dtype == DISTB200_F32) DISTB200_LN(float, 8); else DISTB200_LN(bf16, 8);
-    } else {
-        if (out_dtype == DISTB200_F32) DISTB200_LN(float, 32); else DISTB200_LN(bf16, 32);
-    }
+#define DISTB200_LN_T(T)                                                                                                             \
+    do {                                                                                                                             \
+        if (cols <= 128) DISTB200_LN(T, 8, 4);                                                                                        \
+        else if (cols <= 256) DISTB200_LN(T, 32, 2);                                                                                  \
+        else if (cols <= 384) DISTB200_LN(T, 32, 3);                                                                                  \
+        else if (cols <= 512) DISTB200_LN(T, 32, 4);                                                                                  \
+        else if (cols <= 768) DISTB200_LN(T, 32, 6);                                                                                  \
+        else DISTB200_LN(T, 32, 8);                                                                                                   \
+    } while (0)
+    // the register footprint (and with it the number of resident warps) follows the row width
+    if (out_dtype == DISTB200_F32) DISTB200_LN_T(float); else DISTB200_LN_T(bf16);
+#undef DISTB200_LN_T
 #undef DISTB200_LN
     return check_launch("layernorm");
 }
@@ -350,6 +404,35 @@ extern "C" int distb200_patchify(const float* video, void* out, int32_t clips, i
     }
 #undef DISTB200_PATCHIFY
     return check_launch("patchify");
+}
+
+
+extern "C" int distb200_patchify_u8(const uint8_t* frames, void* out, int32_t clips, int32_t T, int32_t H, int32_t W, int32_t p,
+                                    int32_t first_frame, int32_t frame_step, int32_t n_sel, int64_t ld_out, int32_t out_dtype,
+                                    const float* mean3, const float* std3, void* stream) {
+    DISTB200_REQUIRE(frames && out && mean3 && std3, "patchify_u8: null pointer");
+    DISTB200_REQUIRE(H % p == 0 && W % p == 0 && W % 2 == 0 && p % 2 == 0, "patchify_u8: H=%d W=%d p=%d", H, W, p);
+    DISTB200_REQUIRE(first_frame >= 0 && frame_step >= 1 && first_frame + (n_sel - 1) * frame_step < T, "patchify_u8: frame selection out of range");
+    DISTB200_REQUIRE(ld_out >= 3 * p * p, "patchify_u8: ld_out too small");
+    DISTB200_REQUIRE((reinterpret_cast<uintptr_t>(frames) & 3) == 0, "patchify_u8: frames must be 4-byte aligned");
+    const long long img_rows = (long long)clips * n_sel * H;
+    if (img_rows == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long rows = (long long)clips * n_sel * (H / p) * (W / p);
+    const bool v4 = p % 4 == 0 && W % 4 == 0 && ld_out % 4 == 0;
+#define DISTB200_PATCHIFY_U8(T_, VEC, TPR)                                                                                          \
+    patchify_u8_kernel<T_, VEC, TPR><<<grid_for(img_rows * TPR, 256), 256, 0, st>>>(frames, (T_*)out, clips, T, H, W, p, first_frame, \
+                                                                                   frame_step, n_sel, ld_out, mean3[0], mean3[1],  \
+                                                                                   mean3[2], std3[0], std3[1], std3[2])
+    if (out_dtype == DISTB200_F32) {
+        if (v4) DISTB200_PATCHIFY_U8(float, 4, 64); else DISTB200_PATCHIFY_U8(float, 2, 128);
+        if (ld_out > 3 * p * p) zero_pad_cols_kernel<float><<<grid_for(rows * (ld_out - 3 * p * p), 256), 256, 0, st>>>((float*)out, rows, 3 * p * p, ld_out);
+    } else {
+        if (v4) DISTB200_PATCHIFY_U8(bf16, 4, 64); else DISTB200_PATCHIFY_U8(bf16, 2, 128);
+        if (ld_out > 3 * p * p) zero_pad_cols_kernel<bf16><<<grid_for(rows * (ld_out - 3 * p * p), 256), 256, 0, st>>>((bf16*)out, rows, 3 * p * p, ld_out);
+    }
+#undef DISTB200_PATCHIFY_U8
+    return check_launch("patchify_u8");
 }
 
 extern "C" int distb200_rows_bcast(float* dst, int64_t row_stride, int64_t n_rows, int32_t cols, const float* table, int64_t period,

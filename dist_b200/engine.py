@@ -125,9 +125,17 @@ class PackedWeights:
 class DistEngine:
     """Planned forward for a fixed number of clips per call."""
 
+    # CLIP normalisation (DATA.MEAN / DATA.STD, configs/projects/dist/vit_base_16_ssv2.yaml:31-32)
+    CLIP_MEAN = (0.48145466, 0.4578275, 0.40821073)
+    CLIP_STD = (0.26862954, 0.26130258, 0.27577711)
+
     def __init__(self, state_dict, arch: DistArch, batch, device="cuda", precision="bf16", text_features=None,
-                 gemm_impl=ops.IMPL_AUTO, attn_impl=ops.IMPL_AUTO):
-        assert precision in ("bf16", "fp32")
+                 gemm_impl=ops.IMPL_AUTO, attn_impl=ops.IMPL_AUTO, input_format="float", mean=None, std=None):
+        """``input_format="uint8"``: clips arrive as decoded frames ``[b, T, H, W, 3]`` uint8 and ToTensorVideo +
+        NormalizeVideo (``dataset/base/ssv2.py:137-143``) are fused into the patch-row kernel."""
+        assert precision in ("bf16", "fp32") and input_format in ("float", "uint8")
+        self.input_format = input_format
+        self.mean, self.std = tuple(mean or self.CLIP_MEAN), tuple(std or self.CLIP_STD)
         arch.validate()
         ops.lib()     # fail loudly before touching the GPU if the extension is missing
         self.arch, self.batch, self.device, self.precision = arch, int(batch), torch.device(device), precision
@@ -157,7 +165,10 @@ class DistEngine:
         Mv, Mt = F * N, b * T * P
         z = lambda *s, dtype=adt: torch.zeros(*s, device=dev, dtype=dtype)
         f32 = torch.float32
-        self.video = z(b, 3, T, a.resolution, a.resolution, dtype=f32)
+        if self.input_format == "uint8":
+            self.video = z(b, T, a.resolution, a.resolution, 3, dtype=torch.uint8)
+        else:
+            self.video = z(b, 3, T, a.resolution, a.resolution, dtype=f32)
         self.patches_s = z(F * P, self.w.kp) if a.patch != a.s_patch else None
         self.patches_d = z(b * T * P, self.w.kps)
         self.h = z(Mv, D, dtype=f32)
@@ -214,10 +225,14 @@ class DistEngine:
 
         # ---- patch rows: sparse frames for the ViT (clip.py:271 restricted to the frames kept at :281-284),
         #      all frames for the temporal stem (dist.py:225)
-        add(ops.patchify(self.video, self.patches_d, b, T, R, R, a.s_patch, 0, 1, T, w.kps, name="patchify.dense"))
+        if self.input_format == "uint8":
+            cut = lambda *args, **kw: ops.patchify_u8(*args, self.mean, self.std, **kw)
+        else:
+            cut = ops.patchify
+        add(cut(self.video, self.patches_d, b, T, R, R, a.s_patch, 0, 1, T, w.kps, name="patchify.dense"))
         shared = a.patch == a.s_patch          # then the ViT's patches are the rows of every alpha-th dense frame
         if not shared:
-            add(ops.patchify(self.video, self.patches_s, b, T, R, R, a.patch, 0, al, t, w.kp, name="patchify.sparse"))
+            add(cut(self.video, self.patches_s, b, T, R, R, a.patch, 0, al, t, w.kp, name="patchify.sparse"))
 
         # ---- ViT embedding: conv1 as GEMM, + positional embedding, class row, ln_pre (clip.py:271-276)
         k1 = 3 * a.patch * a.patch
@@ -310,9 +325,11 @@ class DistEngine:
         add(ops.rows_bcast(self.mid, N * Ci, F, Ci, d["t2i_cls"], t, True, name="dist.t2i.cls"))
 
         # ---- integration -> temporal (dist.py:90-105,231): patch tokens only, nearest upsample = row replication
-        self._gemm(self.mid_a, d["i2t_w"], Ct, Ci, a_dim=(Ci, N, F, 1), a_stride=(1, Ci, N * Ci, Mv * Ci), taps=[(1, 0, 0)],
-                   groups=F, rows_per_group=P, ldb=Ci, bias=d["i2t_b"], res=self.xT, ld_res=Ct, res_gstride=al * P,
-                   res_rep_stride=P, out=self.xT, ld_out=Ct, out_gstride=al * P, out_rep=al, out_rep_stride=P, name="dist.i2t")
+        # (the fused temporal stream of the LAST layer is read by nothing, dist.py:231-235: its branch is skipped)
+        if i < len(a.selected_layers) - 1:
+            self._gemm(self.mid_a, d["i2t_w"], Ct, Ci, a_dim=(Ci, N, F, 1), a_stride=(1, Ci, N * Ci, Mv * Ci), taps=[(1, 0, 0)],
+                       groups=F, rows_per_group=P, ldb=Ci, bias=d["i2t_b"], res=self.xT, ld_res=Ct, res_gstride=al * P,
+                       res_rep_stride=P, out=self.xT, ld_out=Ct, out_gstride=al * P, out_rep=al, out_rep_stride=P, name="dist.i2t")
 
         # ---- IntegrationNetwork (dist.py:16-45) on upd = mid ----
         add(ops.layernorm(self.mid, d["ln"][0], d["ln"][1], self.int_a1, g2=d["ln_t"][0], b2=d["ln_t"][1], y2=self.int_a2,
@@ -397,7 +414,8 @@ class DistEngine:
         return graph
 
     def forward(self, video=None, use_graph=True):
-        """video [b, 3, T, H, W] fp32 (host or device) -> embedding [b, E] fp32 (view of an internal buffer)."""
+        """video [b, 3, T, H, W] fp32 - or [b, T, H, W, 3] uint8 for ``input_format="uint8"`` - (host or device)
+        -> embedding [b, E] fp32 (view of an internal buffer)."""
         if video is not None:
             assert tuple(video.shape) == tuple(self.video.shape), (video.shape, self.video.shape)
             self.video.copy_(video, non_blocking=True)

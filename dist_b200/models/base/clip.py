@@ -138,16 +138,17 @@ class CLIP(nn.Module):
             "forward path (SURVEY.md section 8f) - call set_text_features([C, E]) with embeddings computed once")
 
     # ---- engine cache -------------------------------------------------------------------------
-    def _engine(self, batch, device, text):
+    def _engine(self, batch, device, text, input_format="float"):
         from ...engine import DistEngine
         version = sum(p._version for p in self.parameters())
         tkey = None if text is None else (text.data_ptr(), tuple(text.shape), text._version)
-        key = (batch, str(device), self.precision)
+        key = (batch, str(device), self.precision, input_format)
         hit = self._engines.get(key)
         if hit is not None and hit[1] == version and hit[2] == tkey:
             return hit[0]
         sd = {k: v for k, v in self.state_dict().items()}
-        eng = DistEngine(sd, self.arch, batch, device=device, precision=self.precision, text_features=text)
+        eng = DistEngine(sd, self.arch, batch, device=device, precision=self.precision, text_features=text, input_format=input_format,
+                         mean=getattr(self.cfg.DATA, "MEAN", None), std=getattr(self.cfg.DATA, "STD", None))
         if self.use_graph:
             eng.capture()
         self._engines[key] = (eng, version, tkey)
@@ -163,7 +164,12 @@ class CLIP(nn.Module):
         return self.forward_without_text(image)
 
     def _as_clips(self, image):
-        """Accept the reference's frame-major ``[B*T,3,H,W]`` (clip.py:460) or the native ``[B,3,T,H,W]``."""
+        """Accept the reference's frame-major ``[B*T,3,H,W]`` (clip.py:460), the native ``[B,3,T,H,W]``, or decoded uint8
+        frames ``[B,T,H,W,3]`` (normalised inside the patch-row kernel with DATA.MEAN / DATA.STD)."""
+        if image.dtype == torch.uint8:
+            if image.dim() != 5 or image.shape[-1] != 3:
+                raise ValueError("uint8 clips must be [B, T, H, W, 3] (decoder layout), got {}".format(tuple(image.shape)))
+            return image
         if image.dim() == 4:
             bt, c, h, w = image.shape
             image = image.view(bt // self.num_frames, self.num_frames, c, h, w).permute(0, 2, 1, 3, 4).contiguous()
@@ -180,15 +186,17 @@ class CLIP(nn.Module):
 
     def forward_without_text(self, image):
         clips = self._as_clips(image)
-        eng = self._engine(clips.shape[0], self._device_for(image), None)
-        emb = eng.forward(clips.float(), use_graph=self.use_graph)
+        u8 = clips.dtype == torch.uint8
+        eng = self._engine(clips.shape[0], self._device_for(image), None, "uint8" if u8 else "float")
+        emb = eng.forward(clips if u8 else clips.float(), use_graph=self.use_graph)
         return emb.clone()[:, None, :]                                       # clip.py:480
 
     def forward_with_text(self, image, text, others=None):
         clips = self._as_clips(image)
         feats = self._text_from(text, others)
-        eng = self._engine(clips.shape[0], self._device_for(image), feats)
-        emb = eng.forward(clips.float(), use_graph=self.use_graph)
+        u8 = clips.dtype == torch.uint8
+        eng = self._engine(clips.shape[0], self._device_for(image), feats, "uint8" if u8 else "float")
+        emb = eng.forward(clips if u8 else clips.float(), use_graph=self.use_graph)
         logits = eng.logits.clone()
         vid = emb / emb.norm(dim=1, keepdim=True)                           # clip.py:513 (returned, not on the scored path)
         return {"logits_per_image": logits, "logits_per_text": logits.t(), "probs_per_image": eng.probs.clone(),
@@ -215,13 +223,8 @@ def load(cfg):
     if local and os.path.exists(local):
         path = local
     if path and os.path.exists(path):
-        if path.endswith(".pyth") or path.endswith(".pth"):
-            state_dict = torch.load(path, map_location="cpu")
-            if "model_state" in state_dict:
-                state_dict = {k.replace("backbone.base_encoder.", ""): v for k, v in state_dict["model_state"].items()}
-        else:
-            state_dict = torch.jit.load(path, map_location="cpu").state_dict()
-        return build_model(cfg, state_dict)
+        from ...utils.checkpoint import load_state_dict
+        return build_model(cfg, load_state_dict(path))
     # "random initialization, only for debugging" (utils/checkpoint.py:524-527)
     arch = arch_from_cfg(cfg)
     seed = int(getattr(cfg, "RANDOM_SEED", 0))

@@ -87,6 +87,7 @@ def lib():
     L.distb200_attention.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp]
     L.distb200_cross_attention.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp]
     L.distb200_patchify.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i64, i32, vp]
+    L.distb200_patchify_u8.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i64, i32, C.POINTER(C.c_float * 3), C.POINTER(C.c_float * 3), vp]
     L.distb200_rows_bcast.argtypes = [vp, i64, i64, i32, vp, i64, i32, vp]
     L.distb200_mean_rows.argtypes = [vp, i64, i32, i64, i32, vp, i32, vp]
     L.distb200_class_head.argtypes = [vp, vp, f32, i32, i32, i32, vp, vp, vp]
@@ -105,7 +106,7 @@ def lib():
     L.distb200_pack_weight.argtypes = [vp, i64, i32, i32, vp, i64, vp, i64, i32, vp]
     for name in TRAIN_EXPORTS:
         getattr(L, name).restype = C.c_int
-    for name in ("gemm", "layernorm", "attention", "cross_attention", "patchify", "rows_bcast", "mean_rows", "class_head"):
+    for name in ("gemm", "layernorm", "attention", "cross_attention", "patchify", "patchify_u8", "rows_bcast", "mean_rows", "class_head"):
         getattr(L, "distb200_" + name).restype = C.c_int
     assert L.distb200_version() == 100 and L.distb200_arch() == 100
     _LIB = L
@@ -117,7 +118,7 @@ TRAIN_EXPORTS = ("distb200_gemm_wgrad", "distb200_quickgelu", "distb200_quickgel
                  "distb200_adamw", "distb200_pack_weight")
 
 EXPORTS = TRAIN_EXPORTS + ("distb200_version", "distb200_arch", "distb200_last_error", "distb200_gemm", "distb200_layernorm",
-           "distb200_attention", "distb200_cross_attention", "distb200_patchify", "distb200_rows_bcast",
+           "distb200_attention", "distb200_cross_attention", "distb200_patchify", "distb200_patchify_u8", "distb200_rows_bcast",
            "distb200_mean_rows", "distb200_class_head")
 
 
@@ -246,6 +247,16 @@ def patchify(video, out, clips, T, H, W, p, first, step, n_sel, ld_out, name="pa
             int(ld_out), enum_of(out))
     px = clips * n_sel * 3 * H * W
     return Call(lib().distb200_patchify, args, name, keep=(video, out), nbytes=px * (4 + out.element_size()))
+
+
+def patchify_u8(frames, out, clips, T, H, W, p, first, step, n_sel, ld_out, mean, std, name="patchify_u8"):
+    """frames uint8 [clips, T, H, W, 3]; mean / std: three floats each (DATA.MEAN / DATA.STD)"""
+    assert frames.dtype == torch.uint8 and frames.is_contiguous()
+    m3, s3 = (C.c_float * 3)(*[float(v) for v in mean]), (C.c_float * 3)(*[float(v) for v in std])
+    args = (frames.data_ptr(), out.data_ptr(), int(clips), int(T), int(H), int(W), int(p), int(first), int(step), int(n_sel),
+            int(ld_out), enum_of(out), C.byref(m3), C.byref(s3))
+    px = clips * n_sel * 3 * H * W
+    return Call(lib().distb200_patchify_u8, args, name, keep=(frames, out, m3, s3), nbytes=px * (1 + out.element_size()))
 
 
 def rows_bcast(dst, row_stride, n_rows, cols, table, period, accumulate, name="rows_bcast"):

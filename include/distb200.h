@@ -131,6 +131,14 @@ int distb200_patchify(const float* video, void* out, int32_t clips, int32_t T, i
                       int32_t first_frame, int32_t frame_step, int32_t n_sel, int64_t ld_out, int32_t out_dtype,
                       void* stream);
 
+/* The same patch rows straight from decoded frames: frames uint8 [clips, T, H, W, 3] (the layout before
+ * transforms.ToTensorVideo, dataset/base/ssv2.py:137), with ToTensorVideo + NormalizeVideo fused in:
+ * value = ((float)u8 / 255 - mean[c]) / std[c]  (DATA.MEAN / DATA.STD, ssv2.py:139-143).  mean3 / std3 are HOST pointers to
+ * three floats.  A quarter of the bytes of the float clip cross PCIe / HBM. */
+int distb200_patchify_u8(const uint8_t* frames, void* out, int32_t clips, int32_t T, int32_t H, int32_t W, int32_t p,
+                         int32_t first_frame, int32_t frame_step, int32_t n_sel, int64_t ld_out, int32_t out_dtype,
+                         const float* mean3, const float* std3, void* stream);
+
 /* dst[i*row_stride + c] = (accumulate ? dst[...] : 0) + table[(i % period)*cols + c], i < n_rows (fp32).
  * Class-token rows (clip.py:274), per-frame cls tokens of dist.py:84, broadcast of the aggregated tokens (dist.py:237-238). */
 int distb200_rows_bcast(float* dst, int64_t row_stride, int64_t n_rows, int32_t cols, const float* table,

@@ -254,3 +254,23 @@ def test_small_kernels():
     _run(ops.class_head(emb, text_n, 14.2857, 5, 64, 11, logits, probs))
     exp = 14.2857 * (emb.double() / emb.double().norm(dim=1, keepdim=True)) @ text_n.double().t()
     assert rel_l2(logits, exp) < 2e-6 and rel_l2(probs, torch.softmax(exp, -1)) < 2e-6
+
+
+@pytest.mark.parametrize("p,dt", [(16, torch.float32), (16, torch.bfloat16), (14, torch.float32), (14, torch.bfloat16)])
+def test_patchify_u8_matches_to_tensor_normalize_patchify(p, dt):
+    """uint8 frames [b, T, H, W, 3] -> the patch rows of (x / 255 - mean) / std (torchvision to_tensor + normalize, ssv2.py:137-143)."""
+    ops = _ops()
+    b, T, R = 2, 4, 8 * p
+    g = torch.Generator().manual_seed(p)
+    frames = torch.randint(0, 256, (b, T, R, R, 3), generator=g, dtype=torch.uint8).to(DEV)
+    mean, std = (0.48145466, 0.4578275, 0.40821073), (0.26862954, 0.26130258, 0.27577711)
+    # the reference normalises on the CPU inside the data loader (true division; CUDA torch multiplies by 1/255 instead)
+    clip = frames.cpu().float().permute(0, 4, 1, 2, 3) / 255.0                                    # [b, 3, T, H, W]
+    clip = ((clip - torch.tensor(mean)[None, :, None, None, None]) / torch.tensor(std)[None, :, None, None, None]).contiguous().to(DEV)
+    ld = (3 * p * p + 7) // 8 * 8
+    for first, step, n_sel in ((0, 1, T), (0, 2, T // 2)):
+        want = torch.full((b * n_sel * 64, ld), 3.0, device=DEV, dtype=dt)
+        got = torch.full((b * n_sel * 64, ld), 3.0, device=DEV, dtype=dt)
+        _run(ops.patchify(clip, want, b, T, R, R, p, first, step, n_sel, ld))
+        _run(ops.patchify_u8(frames, got, b, T, R, R, p, first, step, n_sel, ld, mean, std))
+        assert torch.equal(got, want)                                                             # same operation order: bit-exact

@@ -121,3 +121,22 @@ def test_registry_driven_model_end_to_end():
     assert torch.allclose(preds.sum(-1), torch.ones(2, device="cuda"), atol=1e-4)
     emb = enc.forward_without_text(clips.permute(0, 2, 1, 3, 4).reshape(-1, 3, 224, 224).cuda())   # reference layout [B*T,3,H,W]
     assert emb.shape == (2, 1, 512) and rel_l2(emb[:, 0], fix["emb"]) < BF16_BAR
+
+
+def test_uint8_clips_equal_normalised_float_clips():
+    """Decoded uint8 frames through the fused normalise + patchify kernel give the same embedding, bit for bit, as the
+    float clip torchvision's ToTensorVideo + NormalizeVideo would have produced."""
+    from dist_b200.engine import DistEngine
+    fix = load_golden("tiny_scaled")
+    arch, sd, _, text = inputs_for(fix)
+    g = torch.Generator().manual_seed(5)
+    frames = torch.randint(0, 256, (2, arch.frames, arch.resolution, arch.resolution, 3), generator=g, dtype=torch.uint8)
+    mean, std = torch.tensor(DistEngine.CLIP_MEAN), torch.tensor(DistEngine.CLIP_STD)
+    clip = ((frames.float().permute(0, 4, 1, 2, 3) / 255.0 - mean[None, :, None, None, None]) / std[None, :, None, None, None]).contiguous()
+    for precision in ("fp32", "bf16"):
+        e_f = DistEngine(sd, arch, 2, precision=precision, text_features=text)
+        e_u = DistEngine(sd, arch, 2, precision=precision, text_features=text, input_format="uint8")
+        a = e_f.forward(clip.cuda(), use_graph=False).clone()
+        b = e_u.forward(frames.cuda(), use_graph=False).clone()
+        torch.cuda.synchronize()
+        assert torch.equal(a, b), precision

@@ -155,3 +155,32 @@ def test_c_abi_exports_every_declared_symbol():
         sizes = [int(x) for x in subprocess.check_output([os.path.join(td, "t")]).split()]
     D = ops.GemmDesc
     assert sizes == [ctypes.sizeof(D), D.ldb.offset, D.out.offset, D.group_dim.offset]
+
+
+def test_checkpoint_ingest_roundtrip_and_legacy_names(tmp_path):
+    """`.pyth` files with the BaseVideoModel prefix, and pre-release `ladder_net.*` names (process_dist_cpkt.py:10-30)."""
+    import torch
+    from dist_b200.arch import tiny_arch
+    from dist_b200.utils import checkpoint, synth
+    arch = tiny_arch()
+    sd = synth.synth_state_dict(arch, seed=0)
+    path = str(tmp_path / "dist.pyth")
+    checkpoint.save_checkpoint(path, sd)
+    raw = torch.load(path, map_location="cpu", weights_only=False)
+    assert all(k.startswith("backbone.base_encoder.") for k in raw["model_state"])
+    back = checkpoint.load_state_dict(path)
+    assert sorted(back) == sorted(sd) and all(torch.equal(back[k], sd[k]) for k in sd)
+    legacy = {}
+    inv = [(new, old) for old, new in checkpoint._LEGACY]
+    for k, v in sd.items():
+        name = k
+        if k.startswith("dist_net."):
+            for new, old in sorted(inv, key=lambda p: -len(p[0])):
+                if name.startswith(new):
+                    name = old + name[len(new):]
+                    break
+        legacy["backbone.base_encoder." + name] = v
+    assert any("ladder_net" in k for k in legacy) and not any("dist_net" in k for k in legacy)
+    torch.save({"model_state": legacy}, path)
+    back = checkpoint.load_state_dict(path)
+    assert sorted(back) == sorted(sd) and all(torch.equal(back[k], sd[k]) for k in sd)
