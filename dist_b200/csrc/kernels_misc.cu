@@ -337,6 +337,47 @@ __global__ void __launch_bounds__(256) class_head_kernel(const float* __restrict
     for (int c = tid; c < C; c += blockDim.x) probs[(long long)b * C + c] = __expf(sl[c] - mx) / den;
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// multi-view ensemble (utils/meters.py:83-115): every clip adds (or max-es) its class scores into the row of its video
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) view_ensemble_kernel(const float* __restrict__ preds, const long long* __restrict__ labels,
+                                                            const long long* __restrict__ clip_ids, int n, int C, int num_clips, int method,
+                                                            float* video_preds, long long* video_labels, long long* clip_count,
+                                                            long long num_videos) {
+    const long long total = (long long)n * C;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(idx / C), c = (int)(idx % C);
+        const long long vid = clip_ids[i] / num_clips;
+        if (vid < 0 || vid >= num_videos) continue;
+        const float v = preds[idx];
+        float* dst = video_preds + vid * C + c;
+        if (method == 0) atomicAdd(dst, v);
+        else atomicMax(reinterpret_cast<int*>(dst), __float_as_int(fmaxf(v, 0.f)));      // scores are probabilities (>= 0): int order = float order
+        if (c == 0) {
+            video_labels[vid] = labels[i];
+            atomicAdd(reinterpret_cast<unsigned long long*>(clip_count + vid), 1ull);
+        }
+    }
+}
+
+// top-k hits (utils/metrics.py topks_correct): a video counts for k when fewer than k classes score strictly higher than its label
+__global__ void __launch_bounds__(256) topk_correct_kernel(const float* __restrict__ video_preds, const long long* __restrict__ video_labels,
+                                                           long long num_videos, int C, const int* __restrict__ ks, int nk, long long* correct) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long vid = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+    if (vid >= num_videos) return;
+    const long long lab = video_labels[vid];
+    if (lab < 0 || lab >= C) return;
+    const float ref = video_preds[vid * C + lab];
+    int higher = 0;
+    for (int c = lane; c < C; c += 32) higher += video_preds[vid * C + c] > ref ? 1 : 0;
+    for (int o = 16; o > 0; o >>= 1) higher += __shfl_xor_sync(0xffffffffu, higher, o);
+    if (lane == 0)
+        for (int j = 0; j < nk; ++j)
+            if (higher < ks[j]) atomicAdd(reinterpret_cast<unsigned long long*>(correct + j), 1ull);
+}
+
 inline unsigned grid_for(long long total, int block) {
     long long g = (total + block - 1) / block;
     const long long cap = (long long)sm_count() * 16;
@@ -433,6 +474,28 @@ extern "C" int distb200_patchify_u8(const uint8_t* frames, void* out, int32_t cl
     }
 #undef DISTB200_PATCHIFY_U8
     return check_launch("patchify_u8");
+}
+
+
+extern "C" int distb200_view_ensemble(const float* preds, const int64_t* labels, const int64_t* clip_ids, int32_t n, int32_t classes,
+                                      int32_t num_clips, int32_t method, float* video_preds, int64_t* video_labels, int64_t* clip_count,
+                                      int64_t num_videos, void* stream) {
+    if (n == 0) return 0;
+    DISTB200_REQUIRE(preds && labels && clip_ids && video_preds && video_labels && clip_count, "view_ensemble: null pointer");
+    DISTB200_REQUIRE(num_clips >= 1 && (method == 0 || method == 1), "view_ensemble: bad arguments");
+    view_ensemble_kernel<<<grid_for((long long)n * classes, 256), 256, 0, (cudaStream_t)stream>>>(
+        preds, (const long long*)labels, (const long long*)clip_ids, n, classes, num_clips, method, video_preds, (long long*)video_labels,
+        (long long*)clip_count, num_videos);
+    return check_launch("view_ensemble");
+}
+
+extern "C" int distb200_topk_correct(const float* video_preds, const int64_t* video_labels, int64_t num_videos, int32_t classes,
+                                     const int32_t* ks, int32_t num_ks, int64_t* correct, void* stream) {
+    if (num_videos == 0 || num_ks == 0) return 0;
+    DISTB200_REQUIRE(video_preds && video_labels && ks && correct, "topk_correct: null pointer");
+    topk_correct_kernel<<<(unsigned)((num_videos + 7) / 8), 256, 0, (cudaStream_t)stream>>>(video_preds, (const long long*)video_labels, num_videos,
+                                                                                       classes, ks, num_ks, (long long*)correct);
+    return check_launch("topk_correct");
 }
 
 extern "C" int distb200_rows_bcast(float* dst, int64_t row_stride, int64_t n_rows, int32_t cols, const float* table, int64_t period,

@@ -88,6 +88,8 @@ def lib():
     L.distb200_cross_attention.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp]
     L.distb200_patchify.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i64, i32, vp]
     L.distb200_patchify_u8.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i64, i32, C.POINTER(C.c_float * 3), C.POINTER(C.c_float * 3), vp]
+    L.distb200_view_ensemble.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, i64, vp]
+    L.distb200_topk_correct.argtypes = [vp, vp, i64, i32, vp, i32, vp, vp]
     L.distb200_rows_bcast.argtypes = [vp, i64, i64, i32, vp, i64, i32, vp]
     L.distb200_mean_rows.argtypes = [vp, i64, i32, i64, i32, vp, i32, vp]
     L.distb200_class_head.argtypes = [vp, vp, f32, i32, i32, i32, vp, vp, vp]
@@ -106,7 +108,8 @@ def lib():
     L.distb200_pack_weight.argtypes = [vp, i64, i32, i32, vp, i64, vp, i64, i32, vp]
     for name in TRAIN_EXPORTS:
         getattr(L, name).restype = C.c_int
-    for name in ("gemm", "layernorm", "attention", "cross_attention", "patchify", "patchify_u8", "rows_bcast", "mean_rows", "class_head"):
+    for name in ("gemm", "layernorm", "attention", "cross_attention", "patchify", "patchify_u8", "rows_bcast", "mean_rows", "class_head", "view_ensemble",
+                 "topk_correct"):
         getattr(L, "distb200_" + name).restype = C.c_int
     assert L.distb200_version() == 100 and L.distb200_arch() == 100
     _LIB = L
@@ -118,7 +121,7 @@ TRAIN_EXPORTS = ("distb200_gemm_wgrad", "distb200_quickgelu", "distb200_quickgel
                  "distb200_adamw", "distb200_pack_weight")
 
 EXPORTS = TRAIN_EXPORTS + ("distb200_version", "distb200_arch", "distb200_last_error", "distb200_gemm", "distb200_layernorm",
-           "distb200_attention", "distb200_cross_attention", "distb200_patchify", "distb200_patchify_u8", "distb200_rows_bcast",
+           "distb200_attention", "distb200_cross_attention", "distb200_patchify", "distb200_patchify_u8", "distb200_view_ensemble", "distb200_topk_correct", "distb200_rows_bcast",
            "distb200_mean_rows", "distb200_class_head")
 
 
@@ -257,6 +260,21 @@ def patchify_u8(frames, out, clips, T, H, W, p, first, step, n_sel, ld_out, mean
             int(ld_out), enum_of(out), C.byref(m3), C.byref(s3))
     px = clips * n_sel * 3 * H * W
     return Call(lib().distb200_patchify_u8, args, name, keep=(frames, out, m3, s3), nbytes=px * (1 + out.element_size()))
+
+
+def view_ensemble(preds, labels, clip_ids, num_clips, method, video_preds, video_labels, clip_count, stream):
+    """Immediate launch (batch sizes vary): accumulate the class scores of a batch of clips into their videos."""
+    assert preds.dtype == torch.float32 and preds.is_contiguous() and labels.dtype == clip_ids.dtype == torch.int64
+    n, c = preds.shape
+    _check(lib().distb200_view_ensemble(preds.data_ptr(), labels.data_ptr(), clip_ids.data_ptr(), int(n), int(c), int(num_clips), int(method),
+                                        video_preds.data_ptr(), video_labels.data_ptr(), clip_count.data_ptr(), int(video_preds.shape[0]),
+                                        stream), "view_ensemble")
+
+
+def topk_correct(video_preds, video_labels, ks_dev, correct, stream):
+    v, c = video_preds.shape
+    _check(lib().distb200_topk_correct(video_preds.data_ptr(), video_labels.data_ptr(), int(v), int(c), ks_dev.data_ptr(), int(ks_dev.numel()),
+                                       correct.data_ptr(), stream), "topk_correct")
 
 
 def rows_bcast(dst, row_stride, n_rows, cols, table, period, accumulate, name="rows_bcast"):

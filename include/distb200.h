@@ -154,6 +154,19 @@ int distb200_class_head(const float* emb, const float* text_n, float scale, int3
                         int32_t classes, float* logits, float* probs, void* stream);
 
 
+/* Multi-view test ensemble on the device (TestMeter.update_stats, utils/meters.py:83-115, without the per-clip Python loop
+ * and the .cpu() synchronisation of runs/test.py:136-145): for every clip i, video = clip_ids[i] / num_clips;
+ * video_preds[video] += preds[i] (method 0, "sum") or = max(video_preds[video], preds[i]) (method 1, "max"; scores >= 0);
+ * video_labels[video] = labels[i]; clip_count[video] += 1.  labels / clip_ids / counts are int64 device arrays. */
+int distb200_view_ensemble(const float* preds, const int64_t* labels, const int64_t* clip_ids, int32_t n, int32_t classes,
+                           int32_t num_clips, int32_t method, float* video_preds, int64_t* video_labels, int64_t* clip_count,
+                           int64_t num_videos, void* stream);
+
+/* correct[j] += #videos whose label is among the ks[j] best scores (utils/metrics.py topks_correct; TestMeter.finalize_metrics,
+ * utils/meters.py:135-163).  ks is a DEVICE array of num_ks ints. */
+int distb200_topk_correct(const float* video_preds, const int64_t* video_labels, int64_t num_videos, int32_t classes,
+                          const int32_t* ks, int32_t num_ks, int64_t* correct, void* stream);
+
 /* ================================================================================================
  * Fine-tuning step (runs/train.py:97-112): the reference gets the backward of
  * the DiST branches from autograd (ATen kernels), the loss from models/utils/losses.py:20-31 and the update

@@ -140,3 +140,78 @@ def test_uint8_clips_equal_normalised_float_clips():
         b = e_u.forward(frames.cuda(), use_graph=False).clone()
         torch.cuda.synchronize()
         assert torch.equal(a, b), precision
+
+
+def _reference_meter(preds, labels, clip_ids, num_videos, num_clips, num_cls, method, ks=(1, 5)):
+    """The reference's TestMeter.update_stats / finalize_metrics loops (utils/meters.py:83-115,135-163) on CPU tensors."""
+    video_preds = torch.zeros(num_videos, num_cls)
+    video_labels = torch.zeros(num_videos).long()
+    clip_count = torch.zeros(num_videos).long()
+    for p, l, c in zip(preds, labels, clip_ids):
+        for ind in range(p.shape[0]):
+            vid = int(c[ind]) // num_clips
+            video_labels[vid] = l[ind]
+            if method == "sum":
+                video_preds[vid] += p[ind]
+            else:
+                video_preds[vid] = torch.max(video_preds[vid], p[ind])
+            clip_count[vid] += 1
+    top = video_preds.topk(max(ks), dim=1).indices                       # utils/metrics.py topks_correct
+    hits = top.eq(video_labels[:, None])
+    return video_preds, video_labels, clip_count, [int(hits[:, :k].any(dim=1).sum()) for k in ks]
+
+
+@pytest.mark.parametrize("method", ["sum", "max"])
+def test_test_meter_matches_reference_loop(method):
+    from dist_b200.meters import TestMeter
+    g = torch.Generator().manual_seed(11)
+    V, K, C = 37, 3, 174
+    order = torch.randperm(V * K, generator=g)[: V * K - 2]              # two clips never arrive
+    batches = order.split(16)
+    labels_all = torch.randint(0, C, (V,), generator=g)
+    meter = TestMeter(None, V, K, C, len(batches), ensemble_method=method)
+    P, L, I = [], [], []
+    for ids in batches:
+        p = torch.softmax(2 * torch.randn(len(ids), C, generator=g), dim=-1)
+        for j, cid in enumerate(ids.tolist()):                            # make the true class likely
+            p[j, labels_all[cid // K]] += 0.2
+        P.append(p), L.append(labels_all[ids // K]), I.append(ids)
+        meter.update_stats(p.cuda(), labels_all[ids // K].cuda(), ids.cuda())
+    stats = meter.finalize_metrics()
+    vp, vl, cc, hits = _reference_meter(P, L, I, V, K, C, method)
+    assert rel_l2(meter.video_preds, vp) < 1e-6
+    assert torch.equal(meter.video_labels.cpu(), vl) and torch.equal(meter.clip_count.cpu(), cc)
+    assert stats["top1_acc"] == "{:.2f}".format(hits[0] / V * 100.0) and stats["top5_acc"] == "{:.2f}".format(hits[1] / V * 100.0)
+
+
+def test_perform_test_multi_view_loop():
+    """runs/test.py semantics end to end on the tiny model: 3 views per video, uint8 clips, scores summed per video."""
+    import dist_b200.models.base  # noqa: F401
+    from dist_b200.engine import DistEngine
+    from dist_b200.meters import TestMeter
+    from dist_b200.runs.test import perform_test
+    fix = load_golden("tiny_scaled")
+    arch, sd, _, text = inputs_for(fix)
+    g = torch.Generator().manual_seed(2)
+    V, K, B = 4, 3, 2
+    frames = torch.randint(0, 256, (V * K, arch.frames, arch.resolution, arch.resolution, 3), generator=g, dtype=torch.uint8)
+    labels = torch.randint(0, arch.num_classes, (V,), generator=g)
+    eng = DistEngine(sd, arch, B, precision="fp32", text_features=text, input_format="uint8")
+
+    class Model(torch.nn.Module):
+        def forward(self, x):
+            eng.forward(x["video"], use_graph=False)
+            return eng.probs.clone(), None
+
+    loader = [({"video": frames[i:i + B]}, {"supervised": labels[torch.arange(i, i + B) // K]}, torch.arange(i, i + B), {}) for i in range(0, V * K, B)]
+    meter = TestMeter(None, V, K, arch.num_classes, len(loader))
+    stats = perform_test(loader, Model(), meter, None)
+    want = torch.zeros(V, arch.num_classes)
+    for i in range(0, V * K, B):
+        eng.forward(frames[i:i + B].cuda(), use_graph=False)
+        for j in range(B):
+            want[(i + j) // K] += eng.probs[j].cpu()
+    assert rel_l2(meter.video_preds, want) < 1e-6
+    assert bool((meter.clip_count == K).all())
+    top1 = float((want.argmax(dim=1) == labels).float().mean()) * 100
+    assert stats["top1_acc"] == "{:.2f}".format(top1)
