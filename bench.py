@@ -362,57 +362,62 @@ def main():
         model.eval()
         enc = model.module.backbone.base_encoder if hasattr(model, "module") else model.backbone.base_encoder
         enc.load_state_dict(sd, strict=True)
-        host = [clips.clone().pin_memory(), clips.flip(0).clone().pin_memory()]
         text_dev = text.to(dev)
         out_host = torch.empty(b, text.shape[0]).pin_memory()
-
-        # Pinned host clips -> device on a copy stream, one step ahead of the compute (what a pin_memory data loader with
-        # .cuda(non_blocking=True) does in runs/test.py:44-70); every step's H2D copy and D2H read are inside the timed region.
         copy_stream = torch.cuda.Stream(dev)
-        dev_buf = [torch.empty_like(clips, device=dev) for _ in range(2)]
-        ready = [torch.cuda.Event() for _ in range(2)]
-        consumed = [torch.cuda.Event() for _ in range(2)]
 
-        def prefetch(i):
-            with torch.cuda.stream(copy_stream):
-                copy_stream.wait_event(consumed[i & 1])
-                dev_buf[i & 1].copy_(host[i & 1], non_blocking=True)
-                ready[i & 1].record(copy_stream)
+        def measure_e2e(host):
+            """Pinned host clips -> device on a copy stream, one step ahead of the compute (what a pin_memory data loader with
+            .cuda(non_blocking=True) does in runs/test.py:44-70); every step's H2D copy and D2H read are inside the timed region."""
+            dev_buf = [torch.empty_like(host[0], device=dev) for _ in range(2)]
+            ready = [torch.cuda.Event() for _ in range(2)]
+            consumed = [torch.cuda.Event() for _ in range(2)]
 
-        for ev in consumed:
-            ev.record(torch.cuda.current_stream())
-        prefetch(0)
+            def prefetch(i):
+                with torch.cuda.stream(copy_stream):
+                    copy_stream.wait_event(consumed[i & 1])
+                    dev_buf[i & 1].copy_(host[i & 1], non_blocking=True)
+                    ready[i & 1].record(copy_stream)
 
-        def e2e_step(i):
-            prefetch(i + 1)
-            torch.cuda.current_stream().wait_event(ready[i & 1])
-            preds, _ = model({"video": dev_buf[i & 1], "texts": text_dev})
-            consumed[i & 1].record(torch.cuda.current_stream())
-            out_host.copy_(preds, non_blocking=False)                        # D2H read of the result (syncs)
+            for ev in consumed:
+                ev.record(torch.cuda.current_stream())
+            prefetch(0)
+
+            def e2e_step(i):
+                prefetch(i + 1)
+                torch.cuda.current_stream().wait_event(ready[i & 1])
+                preds, _ = model({"video": dev_buf[i & 1], "texts": text_dev})
+                consumed[i & 1].record(torch.cuda.current_stream())
+                out_host.copy_(preds, non_blocking=False)                        # D2H read of the result (syncs)
+                if world > 1:
+                    dist.all_gather_into_tensor(gathered, preds.contiguous())
+
+            for i in range(args.warmup):
+                e2e_step(i)
+            torch.cuda.synchronize()
             if world > 1:
-                dist.all_gather_into_tensor(gathered, preds.contiguous())
+                dist.barrier()
+            t0 = time.perf_counter()
+            e0.record()
+            for i in range(args.steps):
+                e2e_step(i)
+            e1.record()
+            torch.cuda.synchronize()
+            wall = time.perf_counter() - t0
+            if world > 1:
+                dist.barrier()
+            ems = torch.tensor([max(e0.elapsed_time(e1), wall * 1e3)], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(ems, op=dist.ReduceOp.MAX)
+            return {"value": world * b * args.steps / (float(ems.item()) / 1e3), "unit": "clips/s",
+                    "h2d_bytes_per_step": int(host[0].numel() * host[0].element_size()), "d2h_bytes_per_step": int(out_host.numel() * 4),
+                    "ms_per_step": float(ems.item()) / args.steps}
 
-        for i in range(args.warmup):
-            e2e_step(i)
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        t0 = time.perf_counter()
-        e0.record()
-        for i in range(args.steps):
-            e2e_step(i)
-        e1.record()
-        torch.cuda.synchronize()
-        wall = time.perf_counter() - t0
-        if world > 1:
-            dist.barrier()
-        ems = torch.tensor([max(e0.elapsed_time(e1), wall * 1e3)], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(ems, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * b * args.steps / (float(ems.item()) / 1e3), "unit": "clips/s",
-               "h2d_bytes_per_step": int(clips.numel() * 4), "d2h_bytes_per_step": int(out_host.numel() * 4),
-               "ms_per_step": float(ems.item()) / args.steps}
-        eng2 = next(iter(enc._engines.values()))[0]
+        e2e = measure_e2e([clips.clone().pin_memory(), clips.flip(0).clone().pin_memory()])
+        # the same call with decoded uint8 frames [b, T, H, W, 3] (normalisation fused into the patch-row kernel): a quarter of the bytes
+        u8 = torch.randint(0, 256, (b, arch.frames, arch.resolution, arch.resolution, 3), dtype=torch.uint8)
+        e2e_u8 = measure_e2e([u8.clone().pin_memory(), u8.flip(0).clone().pin_memory()])
+        eng2 = next(e for k, (e, _, _) in enc._engines.items() if k[3] == "float")
     else:
         eng2 = eng
 
@@ -460,7 +465,7 @@ def main():
             "roofline": roofline,
             "gemm_all": {"launches": fam.get("gemm_vit", {}).get("launches", 0) + fam.get("gemm_dist", {}).get("launches", 0),
                          "achieved": achieved, "unit": "TFLOP/s", "frac": achieved / pk["tf_sustained"]},
-            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": eng.num_launches * args.steps, "launches_per_step": eng.num_launches,
+            "cpu_baseline": cpu, "e2e": e2e, "e2e_uint8_frames": e2e_u8 if e2e is not None else None, "gpu_launches": eng.num_launches * args.steps, "launches_per_step": eng.num_launches,
             "kernels": kernels, "clocks": clocks,
         }
         print(json.dumps(line))
