@@ -12,6 +12,7 @@ constexpr int ATT_WARPS = 8;
 
 template <typename T>
 __global__ void __launch_bounds__(ATT_WARPS * 32) attention_simt_kernel(const T* __restrict__ qkv, T* __restrict__ out, int tokens, int heads) {
+    grid_dep_sync();
     extern __shared__ float smem[];
     const int D = heads * HD;
     const int f = blockIdx.x / heads, h = blockIdx.x % heads;
@@ -74,11 +75,11 @@ int attention_simt_launch(const void* qkv, void* out, int frames, int tokens, in
     if (dtype == DISTB200_F32) {
         static bool done = false;
         if (!done) { cudaFuncSetAttribute(attention_simt_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); done = true; }
-        attention_simt_kernel<float><<<grid, ATT_WARPS * 32, smem, stream>>>((const float*)qkv, (float*)out, tokens, heads);
+        DISTB200_LAUNCH(attention_simt_kernel<float>, grid, ATT_WARPS * 32, smem, stream, (const float*)qkv, (float*)out, tokens, heads);
     } else {
         static bool done = false;
         if (!done) { cudaFuncSetAttribute(attention_simt_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); done = true; }
-        attention_simt_kernel<bf16><<<grid, ATT_WARPS * 32, smem, stream>>>((const bf16*)qkv, (bf16*)out, tokens, heads);
+        DISTB200_LAUNCH(attention_simt_kernel<bf16>, grid, ATT_WARPS * 32, smem, stream, (const bf16*)qkv, (bf16*)out, tokens, heads);
     }
     return check_launch("attention_simt");
 }

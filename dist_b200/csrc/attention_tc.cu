@@ -111,6 +111,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_tc_kernel(const __gr
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem = tmem_slot;
+    grid_dep_sync();          // PDL: the prologue above overlaps the previous kernel's tail
     const int QTn = args.q_tiles;
     const int ns = args.n_slots;
     long long my_items = (args.items - blockIdx.x + gridDim.x - 1) / gridDim.x;
@@ -365,7 +366,7 @@ int attention_tc_launch(const void* qkv, void* out, int frames, int tokens, int 
         smem_set = smem;
     }
     const long long grid = args.items < sm_count() ? args.items : sm_count();
-    attention_tc_kernel<<<(unsigned)grid, ATT_THREADS, smem, stream>>>(args);
+    DISTB200_LAUNCH(attention_tc_kernel, (unsigned)grid, ATT_THREADS, smem, stream, args);
     return check_launch("attention_tc");
 }
 

@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "../../include/distb200.h"
 
@@ -56,6 +57,45 @@ __device__ __forceinline__ float warp_max(float v) {
     for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
 }
+
+// ---- programmatic dependent launch (PDL) --------------------------------------------------------------------------
+// Every kernel of the library can be launched with cudaLaunchAttributeProgrammaticStreamSerialization and starts with
+// grid_dep_sync(): its CTAs may become resident (and run their prologue: barrier init, TMEM allocation, descriptor
+// prefetch) while the previous kernel of the stream drains, and they touch global memory only after that kernel has
+// completed and flushed.  Measured on B200 inside the CUDA graph (B/16 8+16f, 276 launches): 15.60 ms with PDL vs
+// 15.33 ms without - the persistent one-CTA-per-SM kernels leave no room for the next grid until they exit, so only the
+// launch bookkeeping is added.  The attribute is therefore OFF by default (DISTB200_PDL=1 enables it); without it the
+// device-side instructions are no-ops.
+__device__ __forceinline__ void grid_dep_sync() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+inline bool pdl_enabled() {
+    static int on = -1;
+    if (on < 0) {
+        const char* e = getenv("DISTB200_PDL");
+        on = (e && atoi(e) != 0) ? 1 : 0;
+    }
+    return on != 0;
+}
+
+template <typename... KArgs, typename... Args>
+inline void launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);        // errors surface through check_launch()
+}
+#define DISTB200_LAUNCH(kernel, grid, block, smem, stream, ...) \
+    ::distb200::launch_kernel(kernel, dim3(grid), dim3(block), (size_t)(smem), (cudaStream_t)(stream), __VA_ARGS__)
 
 inline int sm_count() {
     static int n = 0;

@@ -16,6 +16,7 @@ struct SimtArgs {
 
 template <typename T>
 __global__ void __launch_bounds__(NT) gemm_simt_kernel(const SimtArgs args) {
+    grid_dep_sync();
     const distb200_gemm_desc& d = args.d;
     __shared__ float As[TK][TM + 4];
     __shared__ float Bs[TK][TN + 4];
@@ -127,6 +128,7 @@ struct WgradSimtArgs {
 
 template <typename T>
 __global__ void __launch_bounds__(WT * WT) wgrad_simt_kernel(const WgradSimtArgs args) {
+    grid_dep_sync();
     const distb200_wgrad_desc& d = args.d;
     __shared__ float Ys[WR][WT + 1];
     __shared__ float Xs[WR][WT + 1];
@@ -185,8 +187,8 @@ int gemm_simt_launch(const distb200_gemm_desc& d, cudaStream_t stream) {
     const long long mt = (args.total_rows + TM - 1) / TM;
     DISTB200_REQUIRE(mt < 2147483647LL, "gemm(simt): too many row tiles (%lld)", mt);
     dim3 grid((unsigned)mt, (unsigned)((d.n + TN - 1) / TN));
-    if (d.dtype == DISTB200_F32) gemm_simt_kernel<float><<<grid, NT, 0, stream>>>(args);
-    else gemm_simt_kernel<bf16><<<grid, NT, 0, stream>>>(args);
+    if (d.dtype == DISTB200_F32) DISTB200_LAUNCH(gemm_simt_kernel<float>, grid, NT, 0, stream, args);
+    else DISTB200_LAUNCH(gemm_simt_kernel<bf16>, grid, NT, 0, stream, args);
     return check_launch("gemm_simt");
 }
 
@@ -206,8 +208,8 @@ int wgrad_simt_launch(const distb200_wgrad_desc& d, cudaStream_t stream) {
     args.rows_per_split = ((args.total_rows + splits - 1) / splits + WR - 1) / WR * WR;
     args.splits = (int)((args.total_rows + args.rows_per_split - 1) / args.rows_per_split);
     dim3 grid((unsigned)(args.n_tiles * d.num_taps), (unsigned)k_tiles, (unsigned)args.splits);
-    if (d.dtype == DISTB200_F32) wgrad_simt_kernel<float><<<grid, WT * WT, 0, stream>>>(args);
-    else wgrad_simt_kernel<bf16><<<grid, WT * WT, 0, stream>>>(args);
+    if (d.dtype == DISTB200_F32) DISTB200_LAUNCH(wgrad_simt_kernel<float>, grid, WT * WT, 0, stream, args);
+    else DISTB200_LAUNCH(wgrad_simt_kernel<bf16>, grid, WT * WT, 0, stream, args);
     return check_launch("wgrad_simt");
 }
 

@@ -354,6 +354,7 @@ __global__ void __launch_bounds__(num_threads(EW), 1) gemm_tcgen05_kernel(const 
     if (CTAS == 2) ptx::cluster_sync(); else __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
+    grid_dep_sync();          // PDL: everything above overlapped the previous kernel's tail; global memory is touched below
 
     const int iters = PROBE(32) ? 1 : d.num_taps * args.k_blocks;
 
@@ -598,22 +599,24 @@ int gemm_tcgen05_launch(const distb200_gemm_desc& d, cudaStream_t stream) {
     cfg.blockDim = dim3((unsigned)num_threads(ew));
     cfg.dynamicSmemBytes = (size_t)smem;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     cfg.attrs = attr;
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.numAttrs = 1;
     cudaError_t e;
     if (args.ctas == 2) {
         long long clusters = args.total_tiles < sm_count() / 2 ? args.total_tiles : sm_count() / 2;
         cfg.gridDim = dim3((unsigned)(2 * clusters));
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = 2;
-        attr[0].val.clusterDim.y = 1;
-        attr[0].val.clusterDim.z = 1;
-        cfg.numAttrs = 1;
+        attr[1].id = cudaLaunchAttributeClusterDimension;
+        attr[1].val.clusterDim.x = 2;
+        attr[1].val.clusterDim.y = 1;
+        attr[1].val.clusterDim.z = 1;
+        cfg.numAttrs = 2;
         e = ew == 8 ? cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<2, 8>, args) : cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<2, 12>, args);
     } else {
         long long grid = args.total_tiles < sm_count() ? args.total_tiles : sm_count();
         cfg.gridDim = dim3((unsigned)grid);
-        cfg.numAttrs = 0;
         e = ew == 8 ? cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<1, 8>, args) : cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<1, 12>, args);
     }
     DISTB200_REQUIRE(e == cudaSuccess, "gemm(tcgen05): launch failed: %s", cudaGetErrorString(e));

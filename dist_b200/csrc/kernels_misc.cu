@@ -31,6 +31,7 @@ __global__ void __launch_bounds__(256, V <= 6 ? 5 : 4) layernorm_kernel(const fl
                                                         long long rows, int cols, float eps,
                                                         const float* __restrict__ g1, const float* __restrict__ b1, OutT* y1, long long ld_y1,
                                                         const float* __restrict__ g2, const float* __restrict__ b2, OutT* y2, long long ld_y2) {
+    grid_dep_sync();
     constexpr int RPW = 32 / LPR;                       // rows per warp
     constexpr int MAXV = V;                             // float4 per lane: cols <= 4 * LPR * V
     const int lane = threadIdx.x & 31, sub = lane % LPR;
@@ -99,6 +100,7 @@ template <> __device__ __forceinline__ void store_pixels<bf16, 2>(bf16* o, const
 template <typename OutT, int VEC, int TPR>
 __global__ void __launch_bounds__(256) patchify_kernel(const float* __restrict__ video, OutT* __restrict__ out, int clips, int T, int H, int W,
                                                        int p, int first, int step, int n_sel, long long ld_out) {
+    grid_dep_sync();
     constexpr int RPB = 256 / TPR;                      // image rows per block
     const int g = W / p;
     const long long n_rows = (long long)clips * n_sel * 3 * H;
@@ -131,6 +133,7 @@ template <typename OutT, int VEC, int TPR>
 __global__ void __launch_bounds__(256) patchify_u8_kernel(const uint8_t* __restrict__ frames, OutT* __restrict__ out, int clips, int T, int H, int W,
                                                           int p, int first, int step, int n_sel, long long ld_out, float m0, float m1, float m2,
                                                           float s0, float s1, float s2) {
+    grid_dep_sync();
     constexpr int RPB = 256 / TPR;
     const int g = W / p;
     const long long n_rows = (long long)clips * n_sel * H;
@@ -172,6 +175,7 @@ __global__ void __launch_bounds__(256) patchify_u8_kernel(const uint8_t* __restr
 
 template <typename OutT>
 __global__ void zero_pad_cols_kernel(OutT* out, long long rows, int c0, long long ld) {
+    grid_dep_sync();
     const int pad = (int)ld - c0;
     const long long total = rows * pad;
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x)
@@ -181,6 +185,7 @@ __global__ void zero_pad_cols_kernel(OutT* out, long long rows, int c0, long lon
 // ---------------------------------------------------------------------------------------------------
 __global__ void rows_bcast_kernel(float* dst, long long row_stride, long long n_rows, int cols, const float* __restrict__ table,
                                   long long period, int accumulate) {
+    grid_dep_sync();
     const long long total = n_rows * cols;
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
         const long long i = idx / cols;
@@ -193,6 +198,7 @@ __global__ void rows_bcast_kernel(float* dst, long long row_stride, long long n_
 
 template <typename OutT>
 __global__ void mean_rows_kernel(const float* __restrict__ src, long long row_stride, int count, long long batch, int cols, OutT* out) {
+    grid_dep_sync();
     const long long total = batch * cols;
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
         const long long b = idx / cols;
@@ -229,6 +235,7 @@ __device__ __forceinline__ void load_row64(const bf16* p, float* v) {
 template <typename T>
 __global__ void __launch_bounds__(128) cross_attention_kernel(const T* __restrict__ q, const T* __restrict__ kv, T* __restrict__ out,
                                                               int batch, int keys, int heads) {
+    grid_dep_sync();
     extern __shared__ float sc_all[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int wpb = blockDim.x >> 5;
@@ -290,6 +297,7 @@ __global__ void __launch_bounds__(128) cross_attention_kernel(const T* __restric
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) class_head_kernel(const float* __restrict__ emb, const float* __restrict__ text_n, float scale,
                                                          int E, int C, float* logits, float* probs) {
+    grid_dep_sync();
     extern __shared__ float sh[];          // [E] embedding, [C] logits, [32] scratch
     float* se = sh;
     float* sl = sh + E;
@@ -345,6 +353,7 @@ __global__ void __launch_bounds__(256) view_ensemble_kernel(const float* __restr
                                                             const long long* __restrict__ clip_ids, int n, int C, int num_clips, int method,
                                                             float* video_preds, long long* video_labels, long long* clip_count,
                                                             long long num_videos) {
+    grid_dep_sync();
     const long long total = (long long)n * C;
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
         const int i = (int)(idx / C), c = (int)(idx % C);
@@ -364,6 +373,7 @@ __global__ void __launch_bounds__(256) view_ensemble_kernel(const float* __restr
 // top-k hits (utils/metrics.py topks_correct): a video counts for k when fewer than k classes score strictly higher than its label
 __global__ void __launch_bounds__(256) topk_correct_kernel(const float* __restrict__ video_preds, const long long* __restrict__ video_labels,
                                                            long long num_videos, int C, const int* __restrict__ ks, int nk, long long* correct) {
+    grid_dep_sync();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long vid = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
     if (vid >= num_videos) return;
@@ -403,7 +413,7 @@ extern "C" int distb200_layernorm(const float* in1, int64_t ld_in1, const float*
     const int wpb = 8;
     cudaStream_t st = (cudaStream_t)stream;
 #define DISTB200_LN(T, LPR, V)                                                                                                      \
-    layernorm_kernel<T, LPR, V><<<(unsigned)((rows + wpb * (32 / LPR) - 1) / (wpb * (32 / LPR))), wpb * 32, 0, st>>>(               \
+    DISTB200_LAUNCH((layernorm_kernel<T, LPR, V>), (unsigned)((rows + wpb * (32 / LPR) - 1) / (wpb * (32 / LPR))), wpb * 32, 0, st,                \
         in1, ld_in1, in2, ld_in2, in2_period, rows, cols, eps, g1, b1, (T*)y1, ld_y1, g2, b2, (T*)y2, ld_y2)
 #define DISTB200_LN_T(T)                                                                                                             \
     do {                                                                                                                             \
@@ -433,15 +443,15 @@ extern "C" int distb200_patchify(const float* video, void* out, int32_t clips, i
     const long long img_rows = (long long)clips * n_sel * 3 * H;
     const bool v4 = p % 4 == 0 && W % 4 == 0 && ld_out % 4 == 0;
 #define DISTB200_PATCHIFY(T, VEC, TPR)                                                                                             \
-    patchify_kernel<T, VEC, TPR><<<grid_for(img_rows * TPR, 256), 256, 0, st>>>(video, (T*)out, clips, T_, H, W, p, first_frame,   \
+    DISTB200_LAUNCH((patchify_kernel<T, VEC, TPR>), grid_for(img_rows * TPR, 256), 256, 0, st, video, (T*)out, clips, T_, H, W, p, first_frame,   \
                                                                                  frame_step, n_sel, ld_out)
     const int T_ = T;
     if (out_dtype == DISTB200_F32) {
         if (v4) DISTB200_PATCHIFY(float, 4, 64); else DISTB200_PATCHIFY(float, 2, 128);
-        if (ld_out > 3 * p * p) zero_pad_cols_kernel<float><<<grid_for(rows * (ld_out - 3 * p * p), 256), 256, 0, st>>>((float*)out, rows, 3 * p * p, ld_out);
+        if (ld_out > 3 * p * p) DISTB200_LAUNCH(zero_pad_cols_kernel<float>, grid_for(rows * (ld_out - 3 * p * p), 256), 256, 0, st, (float*)out, rows, 3 * p * p, ld_out);
     } else {
         if (v4) DISTB200_PATCHIFY(bf16, 4, 64); else DISTB200_PATCHIFY(bf16, 2, 128);
-        if (ld_out > 3 * p * p) zero_pad_cols_kernel<bf16><<<grid_for(rows * (ld_out - 3 * p * p), 256), 256, 0, st>>>((bf16*)out, rows, 3 * p * p, ld_out);
+        if (ld_out > 3 * p * p) DISTB200_LAUNCH(zero_pad_cols_kernel<bf16>, grid_for(rows * (ld_out - 3 * p * p), 256), 256, 0, st, (bf16*)out, rows, 3 * p * p, ld_out);
     }
 #undef DISTB200_PATCHIFY
     return check_launch("patchify");
@@ -462,15 +472,15 @@ extern "C" int distb200_patchify_u8(const uint8_t* frames, void* out, int32_t cl
     const long long rows = (long long)clips * n_sel * (H / p) * (W / p);
     const bool v4 = p % 4 == 0 && W % 4 == 0 && ld_out % 4 == 0;
 #define DISTB200_PATCHIFY_U8(T_, VEC, TPR)                                                                                          \
-    patchify_u8_kernel<T_, VEC, TPR><<<grid_for(img_rows * TPR, 256), 256, 0, st>>>(frames, (T_*)out, clips, T, H, W, p, first_frame, \
+    DISTB200_LAUNCH((patchify_u8_kernel<T_, VEC, TPR>), grid_for(img_rows * TPR, 256), 256, 0, st, frames, (T_*)out, clips, T, H, W, p, first_frame, \
                                                                                    frame_step, n_sel, ld_out, mean3[0], mean3[1],  \
                                                                                    mean3[2], std3[0], std3[1], std3[2])
     if (out_dtype == DISTB200_F32) {
         if (v4) DISTB200_PATCHIFY_U8(float, 4, 64); else DISTB200_PATCHIFY_U8(float, 2, 128);
-        if (ld_out > 3 * p * p) zero_pad_cols_kernel<float><<<grid_for(rows * (ld_out - 3 * p * p), 256), 256, 0, st>>>((float*)out, rows, 3 * p * p, ld_out);
+        if (ld_out > 3 * p * p) DISTB200_LAUNCH(zero_pad_cols_kernel<float>, grid_for(rows * (ld_out - 3 * p * p), 256), 256, 0, st, (float*)out, rows, 3 * p * p, ld_out);
     } else {
         if (v4) DISTB200_PATCHIFY_U8(bf16, 4, 64); else DISTB200_PATCHIFY_U8(bf16, 2, 128);
-        if (ld_out > 3 * p * p) zero_pad_cols_kernel<bf16><<<grid_for(rows * (ld_out - 3 * p * p), 256), 256, 0, st>>>((bf16*)out, rows, 3 * p * p, ld_out);
+        if (ld_out > 3 * p * p) DISTB200_LAUNCH(zero_pad_cols_kernel<bf16>, grid_for(rows * (ld_out - 3 * p * p), 256), 256, 0, st, (bf16*)out, rows, 3 * p * p, ld_out);
     }
 #undef DISTB200_PATCHIFY_U8
     return check_launch("patchify_u8");
@@ -483,7 +493,7 @@ extern "C" int distb200_view_ensemble(const float* preds, const int64_t* labels,
     if (n == 0) return 0;
     DISTB200_REQUIRE(preds && labels && clip_ids && video_preds && video_labels && clip_count, "view_ensemble: null pointer");
     DISTB200_REQUIRE(num_clips >= 1 && (method == 0 || method == 1), "view_ensemble: bad arguments");
-    view_ensemble_kernel<<<grid_for((long long)n * classes, 256), 256, 0, (cudaStream_t)stream>>>(
+    DISTB200_LAUNCH(view_ensemble_kernel, grid_for((long long)n * classes, 256), 256, 0, (cudaStream_t)stream, 
         preds, (const long long*)labels, (const long long*)clip_ids, n, classes, num_clips, method, video_preds, (long long*)video_labels,
         (long long*)clip_count, num_videos);
     return check_launch("view_ensemble");
@@ -493,7 +503,7 @@ extern "C" int distb200_topk_correct(const float* video_preds, const int64_t* vi
                                      const int32_t* ks, int32_t num_ks, int64_t* correct, void* stream) {
     if (num_videos == 0 || num_ks == 0) return 0;
     DISTB200_REQUIRE(video_preds && video_labels && ks && correct, "topk_correct: null pointer");
-    topk_correct_kernel<<<(unsigned)((num_videos + 7) / 8), 256, 0, (cudaStream_t)stream>>>(video_preds, (const long long*)video_labels, num_videos,
+    DISTB200_LAUNCH(topk_correct_kernel, (unsigned)((num_videos + 7) / 8), 256, 0, (cudaStream_t)stream, video_preds, (const long long*)video_labels, num_videos,
                                                                                        classes, ks, num_ks, (long long*)correct);
     return check_launch("topk_correct");
 }
@@ -502,7 +512,7 @@ extern "C" int distb200_rows_bcast(float* dst, int64_t row_stride, int64_t n_row
                                    int32_t accumulate, void* stream) {
     if (n_rows == 0 || cols == 0) return 0;
     DISTB200_REQUIRE(period >= 1, "rows_bcast: period must be >= 1");
-    rows_bcast_kernel<<<grid_for(n_rows * cols, 256), 256, 0, (cudaStream_t)stream>>>(dst, row_stride, n_rows, cols, table, period, accumulate);
+    DISTB200_LAUNCH(rows_bcast_kernel, grid_for(n_rows * cols, 256), 256, 0, (cudaStream_t)stream, dst, row_stride, n_rows, cols, table, period, accumulate);
     return check_launch("rows_bcast");
 }
 
@@ -511,8 +521,8 @@ extern "C" int distb200_mean_rows(const float* src, int64_t row_stride, int32_t 
     if (batch == 0 || cols == 0) return 0;
     DISTB200_REQUIRE(count >= 1, "mean_rows: count must be >= 1");
     cudaStream_t st = (cudaStream_t)stream;
-    if (out_dtype == DISTB200_F32) mean_rows_kernel<float><<<grid_for(batch * cols, 256), 256, 0, st>>>(src, row_stride, count, batch, cols, (float*)out);
-    else mean_rows_kernel<bf16><<<grid_for(batch * cols, 256), 256, 0, st>>>(src, row_stride, count, batch, cols, (bf16*)out);
+    if (out_dtype == DISTB200_F32) DISTB200_LAUNCH(mean_rows_kernel<float>, grid_for(batch * cols, 256), 256, 0, st, src, row_stride, count, batch, cols, (float*)out);
+    else DISTB200_LAUNCH(mean_rows_kernel<bf16>, grid_for(batch * cols, 256), 256, 0, st, src, row_stride, count, batch, cols, (bf16*)out);
     return check_launch("mean_rows");
 }
 
@@ -525,8 +535,8 @@ extern "C" int distb200_cross_attention(const void* q, const void* kv, void* out
     const unsigned grid = (unsigned)((items + wpb - 1) / wpb);
     const size_t smem = (size_t)wpb * keys * sizeof(float);
     cudaStream_t st = (cudaStream_t)stream;
-    if (dtype == DISTB200_F32) cross_attention_kernel<float><<<grid, wpb * 32, smem, st>>>((const float*)q, (const float*)kv, (float*)out, batch, keys, heads);
-    else cross_attention_kernel<bf16><<<grid, wpb * 32, smem, st>>>((const bf16*)q, (const bf16*)kv, (bf16*)out, batch, keys, heads);
+    if (dtype == DISTB200_F32) DISTB200_LAUNCH(cross_attention_kernel<float>, grid, wpb * 32, smem, st, (const float*)q, (const float*)kv, (float*)out, batch, keys, heads);
+    else DISTB200_LAUNCH(cross_attention_kernel<bf16>, grid, wpb * 32, smem, st, (const bf16*)q, (const bf16*)kv, (bf16*)out, batch, keys, heads);
     return check_launch("cross_attention");
 }
 
@@ -535,6 +545,6 @@ extern "C" int distb200_class_head(const float* emb, const float* text_n, float 
     if (batch == 0) return 0;
     const size_t smem = (size_t)(embed_dim + classes + 32) * sizeof(float);
     DISTB200_REQUIRE(smem <= 48 * 1024, "class_head: E + C too large for one block (%zu bytes)", smem);
-    class_head_kernel<<<batch, 256, smem, (cudaStream_t)stream>>>(emb, text_n, scale, embed_dim, classes, logits, probs);
+    DISTB200_LAUNCH(class_head_kernel, batch, 256, smem, (cudaStream_t)stream, emb, text_n, scale, embed_dim, classes, logits, probs);
     return check_launch("class_head");
 }

@@ -48,6 +48,7 @@ enum { EW_GELU = 0, EW_GELU_BWD = 1, EW_CAST = 2 };
 template <int OP>
 __global__ void __launch_bounds__(256) elementwise_kernel(const void* a, int a_dtype, const void* b, int b_dtype, float* o32, void* olp,
                                                           int lp_dtype, long long n) {
+    grid_dep_sync();
     const long long n4 = n >> 2;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
         const float4 x = ld4_any(a, a_dtype, 4 * i);
@@ -76,6 +77,7 @@ __global__ void __launch_bounds__(256) elementwise_kernel(const void* a, int a_d
 
 __global__ void __launch_bounds__(256) group_sum_kernel(const void* src, int src_dtype, long long groups, int alpha, long long inner, void* dst,
                                                         int dst_dtype) {
+    grid_dep_sync();
     const long long inner4 = inner >> 2, total = groups * inner4;
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
         const long long g = idx / inner4, i = (idx - g * inner4) * 4;
@@ -95,6 +97,7 @@ __global__ void __launch_bounds__(256) group_sum_kernel(const void* src, int src
 __global__ void __launch_bounds__(256) colsum_kernel(const void* src, int dtype, long long ld, long long groups, long long rows_per_group,
                                                      long long gstride, long long roff, long long period, int cols, float* out, float* out2,
                                                      long long rows_per_block) {
+    grid_dep_sync();
     // thread = 4 consecutive columns (16-byte / 8-byte loads), 32 column vectors x 8 row lanes per block
     __shared__ float4 red[8][33];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -173,6 +176,7 @@ __global__ void __launch_bounds__(LNB_WARPS * 32) layernorm_bwd_kernel(
     float eps, const float* __restrict__ g1, const void* dy1, long long ld_dy1, const float* __restrict__ g2, const void* dy2, long long ld_dy2,
     int dy_dtype, const float* add, long long ld_add, float* dx, long long ld_dx, int accumulate, void* dx_lp, long long ld_dx_lp, int lp_dtype,
     float* dg1, float* db1, float* dg2, float* db2, int rows_per_warp) {
+    grid_dep_sync();
     extern __shared__ float sh[];            // [4][cols]: dg1, db1, dg2, db2 partials of this block
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < 4 * cols; i += blockDim.x) sh[i] = 0.f;
@@ -292,6 +296,7 @@ __global__ void __launch_bounds__(LNB_WARPS * 32) layernorm_bwd_kernel(
 template <typename T>
 __global__ void __launch_bounds__(128) cross_attention_bwd_kernel(const T* __restrict__ q, const T* __restrict__ kv, const T* __restrict__ d_out,
                                                                   T* __restrict__ dq, T* __restrict__ dkv, int batch, int keys, int heads) {
+    grid_dep_sync();
     extern __shared__ float sc_all[];          // per warp: [keys] probabilities, [keys] dp
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
     const long long item = (long long)blockIdx.x * wpb + warp;
@@ -373,6 +378,7 @@ __device__ __forceinline__ float block_max(float v, float* red, int tid) {
 __global__ void __launch_bounds__(256) softce_head_kernel(const float* __restrict__ emb, const float* __restrict__ text_n, float scale,
                                                           const float* __restrict__ target, int batch, int E, int C, float* logits, float* loss,
                                                           float* d_emb) {
+    grid_dep_sync();
     extern __shared__ float sh[];          // [E] unit embedding, [C] logits -> d_logits, [E] u = d_logits . text_n, [32] scratch
     float* se = sh;
     float* sl = sh + E;
@@ -435,6 +441,7 @@ __global__ void __launch_bounds__(256) softce_head_kernel(const float* __restric
 __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                                                     long long n, float lr, float beta1, float beta2, float eps, float decay, float inv_bc1,
                                                     float inv_sqrt_bc2, float grad_scale) {
+    grid_dep_sync();
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const float gi = g[i] * grad_scale;
         const float mi = beta1 * m[i] + (1.f - beta1) * gi;
@@ -450,6 +457,7 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const
 template <typename T>
 __global__ void __launch_bounds__(256) pack_weight_kernel(const float* __restrict__ w, int n, int k, T* out, long long ld_out, T* out_t,
                                                           long long ld_out_t) {
+    grid_dep_sync();
     __shared__ float tile[32][33];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const long long bz = blockIdx.z;
@@ -480,7 +488,7 @@ using namespace distb200;
 extern "C" int distb200_quickgelu(const void* z, int32_t z_dtype, float* y_f32, void* y_lp, int32_t lp_dtype, int64_t n, void* stream) {
     if (n == 0) return 0;
     DISTB200_REQUIRE(z && (y_f32 || y_lp) && DISTB200_DTYPE_OK(z_dtype) && DISTB200_DTYPE_OK(lp_dtype), "quickgelu: bad arguments");
-    elementwise_kernel<EW_GELU><<<grid_cap(n / 4 + 1, 256), 256, 0, (cudaStream_t)stream>>>(z, z_dtype, nullptr, 0, y_f32, y_lp, lp_dtype, n);
+    DISTB200_LAUNCH(elementwise_kernel<EW_GELU>, grid_cap(n / 4 + 1, 256), 256, 0, (cudaStream_t)stream, z, z_dtype, nullptr, 0, y_f32, y_lp, lp_dtype, n);
     return check_launch("quickgelu");
 }
 
@@ -489,14 +497,14 @@ extern "C" int distb200_quickgelu_bwd(const void* dy, int32_t dy_dtype, const vo
     if (n == 0) return 0;
     DISTB200_REQUIRE(dy && z && (dz_f32 || dz_lp) && DISTB200_DTYPE_OK(dy_dtype) && DISTB200_DTYPE_OK(z_dtype) && DISTB200_DTYPE_OK(lp_dtype),
                     "quickgelu_bwd: bad arguments");
-    elementwise_kernel<EW_GELU_BWD><<<grid_cap(n / 4 + 1, 256), 256, 0, (cudaStream_t)stream>>>(dy, dy_dtype, z, z_dtype, dz_f32, dz_lp, lp_dtype, n);
+    DISTB200_LAUNCH(elementwise_kernel<EW_GELU_BWD>, grid_cap(n / 4 + 1, 256), 256, 0, (cudaStream_t)stream, dy, dy_dtype, z, z_dtype, dz_f32, dz_lp, lp_dtype, n);
     return check_launch("quickgelu_bwd");
 }
 
 extern "C" int distb200_cast(const float* src, void* dst, int32_t dst_dtype, int64_t n, void* stream) {
     if (n == 0) return 0;
     DISTB200_REQUIRE(src && dst && DISTB200_DTYPE_OK(dst_dtype), "cast: bad arguments");
-    elementwise_kernel<EW_CAST><<<grid_cap(n / 4 + 1, 256), 256, 0, (cudaStream_t)stream>>>(src, DISTB200_F32, nullptr, 0, nullptr, dst, dst_dtype, n);
+    DISTB200_LAUNCH(elementwise_kernel<EW_CAST>, grid_cap(n / 4 + 1, 256), 256, 0, (cudaStream_t)stream, src, DISTB200_F32, nullptr, 0, nullptr, dst, dst_dtype, n);
     return check_launch("cast");
 }
 
@@ -505,7 +513,7 @@ extern "C" int distb200_group_sum(const void* src, int32_t src_dtype, int64_t gr
     if (groups == 0 || inner == 0) return 0;
     DISTB200_REQUIRE(src && dst && alpha >= 1 && inner % 4 == 0 && DISTB200_DTYPE_OK(src_dtype) && DISTB200_DTYPE_OK(dst_dtype),
                     "group_sum: bad arguments (inner must be a multiple of 4)");
-    group_sum_kernel<<<grid_cap(groups * inner / 4, 256), 256, 0, (cudaStream_t)stream>>>(src, src_dtype, groups, alpha, inner, dst, dst_dtype);
+    DISTB200_LAUNCH(group_sum_kernel, grid_cap(groups * inner / 4, 256), 256, 0, (cudaStream_t)stream, src, src_dtype, groups, alpha, inner, dst, dst_dtype);
     return check_launch("group_sum");
 }
 
@@ -528,7 +536,7 @@ extern "C" int distb200_colsum(const void* src, int32_t src_dtype, int64_t ld, i
     } else {
         grid.y = (unsigned)(period < 65535 ? period : 65535);
     }
-    colsum_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, src_dtype, ld, groups, rows_per_group, gstride, roff, period, cols, out, out2,
+    DISTB200_LAUNCH(colsum_kernel, grid, 256, 0, (cudaStream_t)stream, src, src_dtype, ld, groups, rows_per_group, gstride, roff, period, cols, out, out2,
                                                           rows_per_block);
     return check_launch("colsum");
 }
@@ -555,7 +563,7 @@ extern "C" int distb200_layernorm_bwd(const float* in1, int64_t ld_in1, const fl
     const long long blocks = (rows + (long long)LNB_WARPS * rows_per_warp - 1) / ((long long)LNB_WARPS * rows_per_warp);
     const size_t smem = (size_t)4 * cols * sizeof(float);
 #define DISTB200_LNB(V)                                                                                                                  \
-    layernorm_bwd_kernel<V><<<(unsigned)blocks, LNB_WARPS * 32, smem, (cudaStream_t)stream>>>(                                          \
+    DISTB200_LAUNCH(layernorm_bwd_kernel<V>, (unsigned)blocks, LNB_WARPS * 32, smem, (cudaStream_t)stream,                                           \
         in1, ld_in1, in2, ld_in2, in2_period, rows, cols, eps, g1, dy1, ld_dy1, g2, dy2, ld_dy2, dy_dtype, add, ld_add, dx, ld_dx, accumulate, dx_lp, \
         ld_dx_lp, lp_dtype, dg1, db1, dg2, db2, rows_per_warp)
     // float4 per lane: the register footprint (and with it the number of resident warps) follows the row width
@@ -580,9 +588,9 @@ extern "C" int distb200_cross_attention_bwd(const void* q, const void* kv, const
     const size_t smem = (size_t)wpb * 2 * keys * sizeof(float);
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == DISTB200_F32)
-        cross_attention_bwd_kernel<float><<<grid, wpb * 32, smem, st>>>((const float*)q, (const float*)kv, (const float*)d_out, (float*)dq, (float*)dkv, batch, keys, heads);
+        DISTB200_LAUNCH(cross_attention_bwd_kernel<float>, grid, wpb * 32, smem, st, (const float*)q, (const float*)kv, (const float*)d_out, (float*)dq, (float*)dkv, batch, keys, heads);
     else
-        cross_attention_bwd_kernel<bf16><<<grid, wpb * 32, smem, st>>>((const bf16*)q, (const bf16*)kv, (const bf16*)d_out, (bf16*)dq, (bf16*)dkv, batch, keys, heads);
+        DISTB200_LAUNCH(cross_attention_bwd_kernel<bf16>, grid, wpb * 32, smem, st, (const bf16*)q, (const bf16*)kv, (const bf16*)d_out, (bf16*)dq, (bf16*)dkv, batch, keys, heads);
     return check_launch("cross_attention_bwd");
 }
 
@@ -592,7 +600,7 @@ extern "C" int distb200_softce_head(const float* emb, const float* text_n, float
     DISTB200_REQUIRE(emb && text_n && target && loss && d_emb, "softce_head: null pointer");
     const size_t smem = (size_t)(2 * embed_dim + classes + 32) * sizeof(float);
     DISTB200_REQUIRE(smem <= 48 * 1024, "softce_head: E + C too large for one block (%zu bytes)", smem);
-    softce_head_kernel<<<batch, 256, smem, (cudaStream_t)stream>>>(emb, text_n, scale, target, batch, embed_dim, classes, logits, loss, d_emb);
+    DISTB200_LAUNCH(softce_head_kernel, batch, 256, smem, (cudaStream_t)stream, emb, text_n, scale, target, batch, embed_dim, classes, logits, loss, d_emb);
     return check_launch("softce_head");
 }
 
@@ -601,7 +609,7 @@ extern "C" int distb200_adamw(float* p, const float* g, float* m, float* v, int6
     if (n == 0) return 0;
     DISTB200_REQUIRE(p && g && m && v && step >= 1, "adamw: bad arguments");
     const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
-    adamw_kernel<<<grid_cap(n, 256), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, 1.0f - lr * weight_decay, (float)(1.0 / bc1),
+    DISTB200_LAUNCH(adamw_kernel, grid_cap(n, 256), 256, 0, (cudaStream_t)stream, p, g, m, v, n, lr, beta1, beta2, eps, 1.0f - lr * weight_decay, (float)(1.0 / bc1),
                                                                     (float)(1.0 / sqrt(bc2)), grad_scale);
     return check_launch("adamw");
 }
@@ -614,7 +622,7 @@ extern "C" int distb200_pack_weight(const float* w, int64_t batch, int32_t n, in
     const long long kc = out ? (ld_out > k ? ld_out : k) : k, nc = out_t ? (ld_out_t > n ? ld_out_t : n) : n;
     dim3 grid((unsigned)((kc + 31) / 32), (unsigned)((nc + 31) / 32), (unsigned)batch);
     cudaStream_t st = (cudaStream_t)stream;
-    if (dtype == DISTB200_F32) pack_weight_kernel<float><<<grid, 256, 0, st>>>(w, n, k, (float*)out, ld_out, (float*)out_t, ld_out_t);
-    else pack_weight_kernel<bf16><<<grid, 256, 0, st>>>(w, n, k, (bf16*)out, ld_out, (bf16*)out_t, ld_out_t);
+    if (dtype == DISTB200_F32) DISTB200_LAUNCH(pack_weight_kernel<float>, grid, 256, 0, st, w, n, k, (float*)out, ld_out, (float*)out_t, ld_out_t);
+    else DISTB200_LAUNCH(pack_weight_kernel<bf16>, grid, 256, 0, st, w, n, k, (bf16*)out, ld_out, (bf16*)out_t, ld_out_t);
     return check_launch("pack_weight");
 }

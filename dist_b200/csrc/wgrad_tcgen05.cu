@@ -127,6 +127,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) wgrad_tcgen05_kernel(const __gri
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = tmem_slot;
+    grid_dep_sync();          // PDL: ring clearing, barrier init and TMEM allocation overlapped the previous kernel's tail
 
     const int a_slabs = (min(d.n, W_TM) + 63) / 64;      // dy slabs actually loaded (n < 64 needs one)
     if (warp == 0) {
@@ -317,7 +318,7 @@ int wgrad_tcgen05_launch(const distb200_wgrad_desc& d, cudaStream_t stream) {
         attr_done = true;
     }
     const long long grid = args.items < sm_count() ? args.items : sm_count();
-    wgrad_tcgen05_kernel<<<(unsigned)grid, W_THREADS, smem, stream>>>(args);
+    DISTB200_LAUNCH(wgrad_tcgen05_kernel, (unsigned)grid, W_THREADS, smem, stream, args);
     return check_launch("wgrad_tcgen05");
 }
 
