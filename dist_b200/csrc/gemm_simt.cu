@@ -97,6 +97,7 @@ __global__ void __launch_bounds__(NT) gemm_simt_kernel(const SimtArgs args) {
                 const int n = n0 + tx * 4 + j;
                 if (n >= d.n) continue;
                 float v = acc[i][j];
+                if (d.ln_stats) v = d.ln_stats[2 * orow + 1] * (v - d.ln_stats[2 * orow] * d.ln_wsum[n]);      // folded LayerNorm
                 if (d.bias) v += d.bias[n];
                 if (d.res) v += d.res[rsrc * d.ld_res + n];
                 if (d.act == DISTB200_ACT_QUICKGELU) v = quick_gelu(v);

@@ -112,14 +112,25 @@ __device__ __forceinline__ void stage_block(const uint32_t* acc, float* stage, i
 // Epilogue variants (compile-time so that the inner loop carries no flag tests):
 //   OUT:  0 = fp32 `out`, 1 = bf16 `out`, 2 = fp32 `out` + bf16 `out2`, 3 = anything (runtime flags)
 //   ACT:  0 none, 1 QuickGELU via tanh.approx.f16x2, 2 QuickGELU via ex2 + rcp
-template <int OUT, bool RES, int ACT>
+// LNF: LayerNorm folded into the GEMM (see distb200_gemm_desc.ln_stats): acc -> rstd * (acc - mean * wsum[n]) + bias[n]
+template <int OUT, bool RES, int ACT, bool LNF = false>
 struct Epi {
     // Column domain: eight lanes cover the 32 columns of a row (four adjacent columns = 16 bytes each), the four
     // lane groups take four consecutive rows.  One loop iteration = four rows: 512 B of fp32 (256 B of bf16) per warp
     // instruction, every row a full 128-byte line.
-    static __device__ __forceinline__ void prefetch(const distb200_gemm_desc& d, float4* rv, float4& bias, long long res_row0, int n, int sub,
-                                                    int rows_here, bool col_ok) {
+    static __device__ __forceinline__ void prefetch(const distb200_gemm_desc& d, float4* rv, float4& bias, float4& ws, long long res_row0,
+                                                    long long srow0, int n, int sub, int rows_here, bool col_ok) {
         bias = (d.bias && col_ok) ? __ldg(reinterpret_cast<const float4*>(d.bias + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (LNF) {
+            // per-row (mean, rstd) travel in the (otherwise unused) residual registers; the eight lanes of a row read one address
+            ws = col_ok ? __ldg(reinterpret_cast<const float4*>(d.ln_wsum + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float2* sp = reinterpret_cast<const float2*>(d.ln_stats) + srow0 + sub;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float2 st = 4 * i + sub < rows_here ? __ldg(sp + 4 * i) : make_float2(0.f, 0.f);
+                rv[i] = make_float4(st.x, st.y, 0.f, 0.f);
+            }
+        }
         if (RES) {
             const float* rp = d.res + (res_row0 + sub) * d.ld_res + n;
             const long long step = 4 * d.ld_res;
@@ -133,7 +144,7 @@ struct Epi {
 
     template <bool FULL>
     static __device__ __forceinline__ void finish_rows(const distb200_gemm_desc& d, const float* stage, const float4* rv, const float4 bias,
-                                                       int lane, int n, int rows_here, long long dst_row0) {
+                                                       const float4 ws, int lane, int n, int rows_here, long long dst_row0) {
         const int sub = lane >> 3, chunk = lane & 7;
         char* o1 = nullptr;
         char* o2 = nullptr;
@@ -161,6 +172,10 @@ struct Epi {
         for (int i = 0; i < 8; ++i) {
             const int row = 4 * i + sub;
             float4 v = vv[i];
+            if (LNF) {
+                const float mu = rv[i].x, rs = rv[i].y;
+                v.x = rs * (v.x - mu * ws.x); v.y = rs * (v.y - mu * ws.y); v.z = rs * (v.z - mu * ws.z); v.w = rs * (v.w - mu * ws.w);
+            }
             v.x += bias.x; v.y += bias.y; v.z += bias.z; v.w += bias.w;
             if (RES) {
                 v.x += rv[i].x; v.y += rv[i].y; v.z += rv[i].z; v.w += rv[i].w;
@@ -189,15 +204,15 @@ struct Epi {
     }
 
     static __device__ __forceinline__ void finish(const distb200_gemm_desc& d, const float* stage, const float4* rv, const float4 bias,
-                                                  int lane, int n, int rows_here, long long dst_row0) {
-        if (rows_here >= 32) finish_rows<true>(d, stage, rv, bias, lane, n, rows_here, dst_row0);
-        else finish_rows<false>(d, stage, rv, bias, lane, n, rows_here, dst_row0);
+                                                  const float4 ws, int lane, int n, int rows_here, long long dst_row0) {
+        if (rows_here >= 32) finish_rows<true>(d, stage, rv, bias, ws, lane, n, rows_here, dst_row0);
+        else finish_rows<false>(d, stage, rv, bias, ws, lane, n, rows_here, dst_row0);
     }
 };
 
 // Per-tile quantities of one epilogue warp.
 struct EpiTile {
-    long long dst0, res0;
+    long long dst0, res0, srow0;
     int n0, ncols, rows_valid;
 };
 
@@ -211,6 +226,7 @@ __device__ __forceinline__ EpiTile epi_tile(const TcArgs& args, long long tile, 
     const long long r = (long long)tc.r0 + quad * 32;
     t.dst0 = tc.gi * d.out_gstride + d.out_roff + r;
     t.res0 = tc.gi * d.res_gstride + d.res_roff + r;
+    t.srow0 = tc.gi * d.rows_per_group + r;            // row of the logical A matrix (index of ln_stats)
     t.n0 = tc.n0;
     t.ncols = min(args.block_n, d.n - tc.n0);
     return t;
@@ -220,10 +236,10 @@ __device__ __forceinline__ EpiTile epi_tile(const TcArgs& args, long long tile, 
 // chunk i+1 is requested before chunk i is processed, so that a warp always has one chunk of loads (4 KB) in
 // flight while it transposes, activates and stores another: the epilogue of the narrow, short-K GEMMs is bound by
 // the latency of these loads, not by their bandwidth.
-template <int OUT, bool RES, int ACT, int EW>
+template <int OUT, bool RES, int ACT, int EW, bool LNF = false>
 __device__ __forceinline__ void epilogue_role(const TcArgs& args, uint32_t tmem_base, float* stage, uint32_t tfull0, uint32_t tempty0,
                                               int warp, int lane, long long tile0, long long tile_step, int rank) {
-    typedef Epi<OUT, RES, ACT> E;
+    typedef Epi<OUT, RES, ACT, LNF> E;
     const distb200_gemm_desc& d = args.d;
     const int quad = warp & 3;              // TMEM lanes [32*quad, 32*quad+32) are the ones this warp may read
     const int half = (warp - 2) >> 2;       // which of the alternating 32-column chunks
@@ -235,9 +251,9 @@ __device__ __forceinline__ void epilogue_role(const TcArgs& args, uint32_t tmem_
     EpiTile cur = epi_tile(args, tile, rank, quad);
     int c0 = half * 32;
     constexpr int CSTEP = 32 * (EW / 4);
-    constexpr bool EPI_PIPE_RES = EW <= 8;       // double-buffered residual prefetch only when registers allow
-    float4 rv[8], bias = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (!PROBE(1) && c0 < cur.ncols) E::prefetch(d, rv, bias, cur.res0, cur.n0 + c0 + cl, sub, cur.rows_valid, c0 + cl < cur.ncols);
+    constexpr bool EPI_PIPE_RES = EW <= 8 && !LNF;   // double-buffered residual prefetch only when registers allow
+    float4 rv[8], bias = make_float4(0.f, 0.f, 0.f, 0.f), ws = bias;
+    if (!PROBE(1) && c0 < cur.ncols) E::prefetch(d, rv, bias, ws, cur.res0, cur.srow0, cur.n0 + c0 + cl, sub, cur.rows_valid, c0 + cl < cur.ncols);
     bool waited = false;
     while (true) {
         // ---- next chunk of this warp (possibly in its next tile): request its residual now
@@ -249,10 +265,10 @@ __device__ __forceinline__ void epilogue_role(const TcArgs& args, uint32_t tmem_
             next_c0 = half * 32;
             if (next_tile < args.total_tiles) nxt = epi_tile(args, next_tile, rank, quad);
         }
-        float4 rv2[EPI_PIPE_RES ? 8 : 1], bias2 = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 rv2[EPI_PIPE_RES ? 8 : 1], bias2 = make_float4(0.f, 0.f, 0.f, 0.f), ws2 = bias2;
         const bool have_next = !PROBE(1) && next_tile < args.total_tiles && next_c0 < nxt.ncols;
         if (EPI_PIPE_RES && have_next)
-            E::prefetch(d, rv2, bias2, nxt.res0, nxt.n0 + next_c0 + cl, sub, nxt.rows_valid, next_c0 + cl < nxt.ncols);
+            E::prefetch(d, rv2, bias2, ws2, nxt.res0, nxt.srow0, nxt.n0 + next_c0 + cl, sub, nxt.rows_valid, next_c0 + cl < nxt.ncols);
 
         // ---- current chunk
         if (!waited) {                       // first chunk of the tile (or no chunk at all: still observe the phase)
@@ -275,8 +291,8 @@ __device__ __forceinline__ void epilogue_role(const TcArgs& args, uint32_t tmem_
                 stage_block(acc, stage, lane);
                 __syncwarp();
                 for (int rep = 0; rep < d.out_rep; ++rep) {
-                    if (rep > 0) E::prefetch(d, rv, bias, cur.res0 + (long long)rep * d.res_rep_stride, n, sub, cur.rows_valid, col_ok);
-                    if (col_ok) E::finish(d, stage, rv, bias, lane, n, cur.rows_valid, cur.dst0 + (long long)rep * d.out_rep_stride);
+                    if (rep > 0) E::prefetch(d, rv, bias, ws, cur.res0 + (long long)rep * d.res_rep_stride, cur.srow0, n, sub, cur.rows_valid, col_ok);
+                    if (col_ok) E::finish(d, stage, rv, bias, ws, lane, n, cur.rows_valid, cur.dst0 + (long long)rep * d.out_rep_stride);
                 }
                 __syncwarp();
             }
@@ -298,12 +314,13 @@ __device__ __forceinline__ void epilogue_role(const TcArgs& args, uint32_t tmem_
         cur = nxt;
         if (EPI_PIPE_RES) {
             bias = bias2;
+            ws = ws2;
             if (RES) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) rv[i] = rv2[i];
             }
         } else if (have_next) {
-            E::prefetch(d, rv, bias, cur.res0, cur.n0 + c0 + cl, sub, cur.rows_valid, c0 + cl < cur.ncols);
+            E::prefetch(d, rv, bias, ws, cur.res0, cur.srow0, cur.n0 + c0 + cl, sub, cur.rows_valid, c0 + cl < cur.ncols);
         }
     }
 }
@@ -467,7 +484,10 @@ __global__ void __launch_bounds__(num_threads(EW), 1) gemm_tcgen05_kernel(const 
         const bool f_only = d.out && d.out_dtype == DISTB200_F32 && !d.out2;
         const bool f_and_bf = d.out && d.out_dtype == DISTB200_F32 && d.out2 && d.out2_dtype == DISTB200_BF16;
 #define DISTB200_EPI(OUT, RES, ACT) epilogue_role<OUT, RES, ACT, EW>(args, tmem_base, stage, tf, te, warp, lane, tile0, tile_step, rank)
-        if (bf_only && !d.res && !gelu) DISTB200_EPI(1, false, 0);
+        if (d.ln_stats) {                                  // host side guarantees: bf16 out only, no residual
+            if (gelu) epilogue_role<1, false, 1, EW, true>(args, tmem_base, stage, tf, te, warp, lane, tile0, tile_step, rank);
+            else epilogue_role<1, false, 0, EW, true>(args, tmem_base, stage, tf, te, warp, lane, tile0, tile_step, rank);
+        } else if (bf_only && !d.res && !gelu) DISTB200_EPI(1, false, 0);
         else if (bf_only && !d.res && gelu) DISTB200_EPI(1, false, 1);
         else if (f_only && d.res && !gelu) DISTB200_EPI(0, true, 0);
         else if (f_and_bf && d.res && !gelu) DISTB200_EPI(2, true, 0);
@@ -517,6 +537,12 @@ int gemm_tcgen05_launch(const distb200_gemm_desc& d, cudaStream_t stream) {
     DISTB200_REQUIRE(!d.out2 || ((reinterpret_cast<uintptr_t>(d.out2) & 15) == 0 && d.ld_out2 % 8 == 0),
                     "gemm(tcgen05): out2 must be 16-byte aligned with ld_out2 %% 8 == 0");
     DISTB200_REQUIRE(d.out_rep >= 1, "gemm(tcgen05): out_rep must be >= 1");
+    if (d.ln_stats) {
+        DISTB200_REQUIRE(d.ln_wsum && d.out && d.out_dtype == DISTB200_BF16 && !d.out2 && !d.res && d.out_rep == 1 && d.num_taps == 1,
+                        "gemm(tcgen05): the folded LayerNorm needs ln_wsum, a bf16 `out` only, no residual, one tap");
+        DISTB200_REQUIRE((reinterpret_cast<uintptr_t>(d.ln_stats) & 7) == 0 && (reinterpret_cast<uintptr_t>(d.ln_wsum) & 15) == 0,
+                        "gemm(tcgen05): ln_stats / ln_wsum alignment");
+    }
 
     TcArgs args;
     args.d = d;

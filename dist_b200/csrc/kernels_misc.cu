@@ -86,6 +86,59 @@ __global__ void __launch_bounds__(256, V <= 6 ? 5 : 4) layernorm_kernel(const fl
     }
 }
 
+
+__device__ __forceinline__ void load_row8(const float* p, float* v) {
+    *reinterpret_cast<float4*>(v) = *reinterpret_cast<const float4*>(p);
+    *reinterpret_cast<float4*>(v + 4) = *reinterpret_cast<const float4*>(p + 4);
+}
+__device__ __forceinline__ void load_row8(const bf16* p, float* v) {
+    const uint4 u = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[j]));
+        v[2 * j] = f.x;
+        v[2 * j + 1] = f.y;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// row statistics for the LayerNorm folded into a GEMM: one warp per row, the row in registers, two-pass variance
+// ---------------------------------------------------------------------------------------------------
+template <typename T, int V>
+__global__ void __launch_bounds__(256) row_stats_kernel(const T* __restrict__ x, long long ld, long long rows, int cols, float eps, float2* stats) {
+    grid_dep_sync();
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const T* p = x + row * ld;
+    float v[8 * V];                      // 8 consecutive values (16 bytes of bf16) per lane and step
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+        const int c = (i * 32 + lane) * 8;
+        if (c < cols) {
+            load_row8(p + c, v + 8 * i);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) sum += v[8 * i + j];
+        }
+    }
+    const float mean = warp_sum(sum) / (float)cols;
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+        const int c = (i * 32 + lane) * 8;
+        if (c < cols)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float dlt = v[8 * i + j] - mean;
+                sq += dlt * dlt;
+            }
+    }
+    const float var = warp_sum(sq) / (float)cols;
+    if (lane == 0) stats[row] = make_float2(mean, rsqrtf(var + eps));
+}
+
 // ---------------------------------------------------------------------------------------------------
 // patchify: one group of TPR threads per image row (clip, frame, channel, y); VEC pixels per thread.  Reads are
 // contiguous along the row, writes are VEC*esize contiguous pieces of the patch rows; index arithmetic once per row.
@@ -429,6 +482,23 @@ extern "C" int distb200_layernorm(const float* in1, int64_t ld_in1, const float*
 #undef DISTB200_LN_T
 #undef DISTB200_LN
     return check_launch("layernorm");
+}
+
+
+extern "C" int distb200_row_stats(const void* x, int32_t dtype, int64_t ld, int64_t rows, int32_t cols, float eps, float* stats, void* stream) {
+    if (rows == 0) return 0;
+    DISTB200_REQUIRE(x && stats, "row_stats: null pointer");
+    DISTB200_REQUIRE(cols % 8 == 0 && cols <= 1024 && ld % 8 == 0, "row_stats: cols=%d must be a multiple of 8 and <= 1024 (ld %% 8 == 0)", cols);
+    DISTB200_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(stats) & 7) == 0, "row_stats: alignment");
+    const unsigned grid = (unsigned)((rows + 7) / 8);
+#define DISTB200_RS(T, V) DISTB200_LAUNCH((row_stats_kernel<T, V>), grid, 256, 0, stream, (const T*)x, ld, rows, cols, eps, (float2*)stats)
+    if (dtype == DISTB200_F32) {
+        if (cols <= 256) DISTB200_RS(float, 1); else if (cols <= 512) DISTB200_RS(float, 2); else if (cols <= 768) DISTB200_RS(float, 3); else DISTB200_RS(float, 4);
+    } else {
+        if (cols <= 256) DISTB200_RS(bf16, 1); else if (cols <= 512) DISTB200_RS(bf16, 2); else if (cols <= 768) DISTB200_RS(bf16, 3); else DISTB200_RS(bf16, 4);
+    }
+#undef DISTB200_RS
+    return check_launch("row_stats");
 }
 
 extern "C" int distb200_patchify(const float* video, void* out, int32_t clips, int32_t T, int32_t H, int32_t W, int32_t p,

@@ -16,6 +16,7 @@ Semantics follow SURVEY.md section 8(a'); the reference lines are cited next to 
 """
 
 import math
+import os
 
 import torch
 
@@ -52,9 +53,21 @@ class PackedWeights:
         self.cls_row = f32((sd["visual.class_embedding"].float() + pos[0]).reshape(1, D))      # clip.py:274-275
         self.ln_pre = (f32(sd["visual.ln_pre.weight"]), f32(sd["visual.ln_pre.bias"]))
         self.vit = []
+
+        def folded(w_key, b_key, g_key, beta_key):
+            """LayerNorm folded into the following linear (distb200_gemm_desc.ln_stats): operand W * gamma, its row sums
+            (of the ROUNDED operand, so that the mean term cancels exactly) and the bias W beta + b."""
+            W, bb = sd[w_key].detach().double(), sd[b_key].detach().double()
+            gam, bet = sd[g_key].detach().double(), sd[beta_key].detach().double()
+            wf = (W * gam[None, :]).float().to(device=device).to(act_dtype).contiguous()
+            return wf, wf.float().sum(dim=1).contiguous(), f32(W @ bet + bb)
+
         for l in range(L):
             pre = "visual.transformer.resblocks.%d." % l
+            qf = folded(pre + "attn.in_proj_weight", pre + "attn.in_proj_bias", pre + "ln_1.weight", pre + "ln_1.bias")
+            ff = folded(pre + "mlp.c_fc.weight", pre + "mlp.c_fc.bias", pre + "ln_2.weight", pre + "ln_2.bias")
             self.vit.append(dict(
+                qkv_wf=qf[0], qkv_ws=qf[1], qkv_bf=qf[2], fc1_wf=ff[0], fc1_ws=ff[1], fc1_bf=ff[2],
                 ln1=(f32(sd[pre + "ln_1.weight"]), f32(sd[pre + "ln_1.bias"])),
                 qkv_w=op(sd[pre + "attn.in_proj_weight"]), qkv_b=f32(sd[pre + "attn.in_proj_bias"]),
                 proj_w=op(sd[pre + "attn.out_proj.weight"]), proj_b=f32(sd[pre + "attn.out_proj.bias"]),
@@ -177,6 +190,12 @@ class DistEngine:
         self.attn_out = z(Mv, D)
         self.fc1 = z(Mv, 4 * D)
         self.tap = z(Mv, D) if self.precision == "bf16" else self.h
+        # LayerNorm folded into the QKV / FC1 GEMMs (bf16 path): bf16 copies of the residual stream + per-row statistics
+        self.ln_fold = self.precision == "bf16" and os.environ.get("DISTB200_LN_FOLD", "1") != "0"
+        if self.ln_fold:
+            self.hb_mid = z(Mv, D)
+            self.row_st = z(Mv, 2, dtype=f32)
+        self._hb_prev = None
         self.xT = z(Mt, Ct, dtype=f32)
         self.xT_a = z(Mt, Ct)
         self.xln = z(Mt, Ct)
@@ -207,10 +226,10 @@ class DistEngine:
         kw.setdefault("impl", self.gemm_impl)
         self.calls.append(ops.gemm(*args, **kw))
 
-    def _lin(self, a, w, bias, out, *, res=None, out2=None, act=ops.ACT_NONE, ld_out=None, name="linear"):
+    def _lin(self, a, w, bias, out, *, res=None, out2=None, act=ops.ACT_NONE, ld_out=None, name="linear", **kw):
         """out[M, n] = act(a[M, k] @ w[n, k]^T + bias (+ res)); ``ld_out`` > n writes into a column slice of a wider buffer"""
         n, k = w.shape
-        self._gemm(a, w, n, k, bias=bias, res=res, ld_res=n, out=out, ld_out=ld_out or n, out2=out2, ld_out2=n, act=act, name=name)
+        self._gemm(a, w, n, k, bias=bias, res=res, ld_res=n, out=out, ld_out=ld_out or n, out2=out2, ld_out2=n, act=act, name=name, **kw)
 
     def _ln(self, x, gb, y, **kw):
         self.calls.append(ops.layernorm(x, gb[0], gb[1], y, **kw))
@@ -283,16 +302,36 @@ class DistEngine:
         self._plan_head()
 
     def _plan_vit_layer(self, l, tap_out):
-        """ResidualAttentionBlockMid (clip.py:170-178); ``tap_out`` receives a copy of the block output (the tap)."""
+        """ResidualAttentionBlockMid (clip.py:170-178); ``tap_out`` receives a copy of the block output (the tap).
+
+        bf16 path: ln_1 / ln_2 are folded into the QKV / FC1 GEMMs.  The producing GEMM (FC2 of the previous block,
+        out_proj of this one) writes a bf16 copy of the residual stream next to the fp32 one; ``row_stats`` reads that copy
+        (half the bytes of the fp32 stream, nothing written back) and the consuming GEMM normalises in its epilogue.
+        The first block's ln_1 follows ln_pre, which is no GEMM: it keeps the stand-alone kernel."""
         a, v = self.arch, self.w.vit[l]
         F, N = self.batch * a.sparse_frames, a.tokens
-        self._ln(self.h, v["ln1"], self.ln_buf, name="vit.ln_1")
-        self._lin(self.ln_buf, v["qkv_w"], v["qkv_b"], self.qkv, name="vit.qkv")
-        self.calls.append(ops.attention(self.qkv, self.attn_out, F, N, a.heads, impl=self.attn_impl, name="vit.attention"))
-        self._lin(self.attn_out, v["proj_w"], v["proj_b"], self.h, res=self.h, name="vit.out_proj")
-        self._ln(self.h, v["ln2"], self.ln_buf, name="vit.ln_2")
-        self._lin(self.ln_buf, v["fc1_w"], v["fc1_b"], self.fc1, act=ops.ACT_QUICKGELU, name="vit.fc1")
-        self._lin(self.fc1, v["fc2_w"], v["fc2_b"], self.h, res=self.h, out2=tap_out, name="vit.fc2")
+        add = self.calls.append
+        fold = self.ln_fold
+        if fold and self._hb_prev is not None:
+            add(ops.row_stats(self._hb_prev, self.row_st, name="vit.ln_1.stats"))
+            self._lin(self._hb_prev, v["qkv_wf"], v["qkv_bf"], self.qkv, ln_stats=self.row_st, ln_wsum=v["qkv_ws"], name="vit.qkv")
+        else:
+            self._ln(self.h, v["ln1"], self.ln_buf, name="vit.ln_1")
+            self._lin(self.ln_buf, v["qkv_w"], v["qkv_b"], self.qkv, name="vit.qkv")
+        add(ops.attention(self.qkv, self.attn_out, F, N, a.heads, impl=self.attn_impl, name="vit.attention"))
+        if fold:
+            self._lin(self.attn_out, v["proj_w"], v["proj_b"], self.h, res=self.h, out2=self.hb_mid, name="vit.out_proj")
+            add(ops.row_stats(self.hb_mid, self.row_st, name="vit.ln_2.stats"))
+            self._lin(self.hb_mid, v["fc1_wf"], v["fc1_bf"], self.fc1, act=ops.ACT_QUICKGELU, ln_stats=self.row_st, ln_wsum=v["fc1_ws"],
+                      name="vit.fc1")
+            hb = tap_out if tap_out is not None else self.tap          # bf16 copy of the block output: the tap AND the next block's operand
+            self._lin(self.fc1, v["fc2_w"], v["fc2_b"], self.h, res=self.h, out2=hb, name="vit.fc2")
+            self._hb_prev = hb
+        else:
+            self._lin(self.attn_out, v["proj_w"], v["proj_b"], self.h, res=self.h, name="vit.out_proj")
+            self._ln(self.h, v["ln2"], self.ln_buf, name="vit.ln_2")
+            self._lin(self.ln_buf, v["fc1_w"], v["fc1_b"], self.fc1, act=ops.ACT_QUICKGELU, name="vit.fc1")
+            self._lin(self.fc1, v["fc2_w"], v["fc2_b"], self.h, res=self.h, out2=tap_out, name="vit.fc2")
 
     def _plan_dist_layer(self, i):
         a, b, w = self.arch, self.batch, self.w

@@ -38,6 +38,7 @@ class GemmDesc(C.Structure):
         ("ld_out", C.c_int64), ("out_gstride", C.c_int64), ("out_roff", C.c_int64), ("out_rep_stride", C.c_int64),
         ("out2", C.c_void_p), ("out2_dtype", C.c_int32), ("act", C.c_int32),
         ("ld_out2", C.c_int64), ("block_n", C.c_int32), ("group_dim", C.c_int32),
+        ("ln_stats", C.c_void_p), ("ln_wsum", C.c_void_p),
     ]
 
 
@@ -84,6 +85,7 @@ def lib():
     L.distb200_last_error.restype = C.c_char_p
     L.distb200_gemm.argtypes = [C.POINTER(GemmDesc), vp]
     L.distb200_layernorm.argtypes = [vp, i64, vp, i64, i64, i64, i32, f32, vp, vp, vp, i64, vp, vp, vp, i64, i32, vp]
+    L.distb200_row_stats.argtypes = [vp, i32, i64, i64, i32, f32, vp, vp]
     L.distb200_attention.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp]
     L.distb200_cross_attention.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp]
     L.distb200_patchify.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i64, i32, vp]
@@ -108,7 +110,7 @@ def lib():
     L.distb200_pack_weight.argtypes = [vp, i64, i32, i32, vp, i64, vp, i64, i32, vp]
     for name in TRAIN_EXPORTS:
         getattr(L, name).restype = C.c_int
-    for name in ("gemm", "layernorm", "attention", "cross_attention", "patchify", "patchify_u8", "rows_bcast", "mean_rows", "class_head", "view_ensemble",
+    for name in ("row_stats", "gemm", "layernorm", "attention", "cross_attention", "patchify", "patchify_u8", "rows_bcast", "mean_rows", "class_head", "view_ensemble",
                  "topk_correct"):
         getattr(L, "distb200_" + name).restype = C.c_int
     assert L.distb200_version() == 100 and L.distb200_arch() == 100
@@ -120,7 +122,7 @@ TRAIN_EXPORTS = ("distb200_gemm_wgrad", "distb200_quickgelu", "distb200_quickgel
                  "distb200_colsum", "distb200_layernorm_bwd", "distb200_cross_attention_bwd", "distb200_softce_head",
                  "distb200_adamw", "distb200_pack_weight")
 
-EXPORTS = TRAIN_EXPORTS + ("distb200_version", "distb200_arch", "distb200_last_error", "distb200_gemm", "distb200_layernorm",
+EXPORTS = TRAIN_EXPORTS + ("distb200_version", "distb200_arch", "distb200_last_error", "distb200_gemm", "distb200_row_stats", "distb200_layernorm",
            "distb200_attention", "distb200_cross_attention", "distb200_patchify", "distb200_patchify_u8", "distb200_view_ensemble", "distb200_topk_correct", "distb200_rows_bcast",
            "distb200_mean_rows", "distb200_class_head")
 
@@ -158,7 +160,7 @@ class Call:
 def gemm(a, b, n, k, *, a_dim=None, a_stride=None, taps=((0, 0, 0),), b_tap_stride=0, ldb=None, img_w=0,
          groups=1, rows_per_group=None, group_dim=2, bias=None, res=None, ld_res=0, res_gstride=0, res_roff=0,
          res_rep_stride=0, out=None, ld_out=0, out_gstride=None, out_roff=0, out_rep=1, out_rep_stride=0,
-         out2=None, ld_out2=0, act=ACT_NONE, impl=IMPL_AUTO, block_n=0, name="gemm"):
+         out2=None, ld_out2=0, act=ACT_NONE, impl=IMPL_AUTO, block_n=0, ln_stats=None, ln_wsum=None, name="gemm"):
     """Prepare one ``distb200_gemm`` (see the header for the exact definition).
 
     Defaults describe a plain ``out[M, n] = a[M, k] @ b[n, k]^T``: ``a`` is a 2-D row-major tensor,
@@ -200,6 +202,8 @@ def gemm(a, b, n, k, *, a_dim=None, a_stride=None, taps=((0, 0, 0),), b_tap_stri
     d.out2 = _ptr(out2)
     d.out2_dtype = enum_of(out2) if out2 is not None else F32
     d.act, d.ld_out2, d.block_n = int(act), int(ld_out2), int(block_n)
+    d.ln_stats, d.ln_wsum = _ptr(ln_stats), _ptr(ln_wsum)
+    assert (ln_stats is None) == (ln_wsum is None)
     rows = int(groups) * int(rows_per_group)
     flops = 2 * rows * int(n) * int(k) * len(taps)
     esz = a.element_size()
@@ -210,7 +214,7 @@ def gemm(a, b, n, k, *, a_dim=None, a_stride=None, taps=((0, 0, 0),), b_tap_stri
         nbytes += rows * int(n) * out2.element_size() * int(out_rep)
     if res is not None:
         nbytes += rows * int(n) * 4 * int(out_rep)
-    return Call(lib().distb200_gemm, (C.byref(d),), name, keep=(d, a, b, bias, res, out, out2), flops=flops, nbytes=nbytes)
+    return Call(lib().distb200_gemm, (C.byref(d),), name, keep=(d, a, b, bias, res, out, out2, ln_stats, ln_wsum), flops=flops, nbytes=nbytes)
 
 
 def layernorm(x, g1, b1, y1, *, in2=None, in2_period=1, g2=None, b2=None, y2=None, rows=None, cols=None,
@@ -227,6 +231,15 @@ def layernorm(x, g1, b1, y1, *, in2=None, in2_period=1, g2=None, b2=None, y2=Non
             int(ld_y2 if ld_y2 is not None else cols), enum_of(y1))
     nbytes = rows * cols * (4 + (4 if in2 is not None else 0) + y1.element_size() * (2 if y2 is not None else 1))
     return Call(lib().distb200_layernorm, args, name, keep=(x, in2, g1, b1, y1, g2, b2, y2), nbytes=nbytes)
+
+
+def row_stats(x, stats, rows=None, cols=None, ld=None, eps=1e-5, name="row_stats"):
+    """(mean, rstd) per row of ``x`` -> ``stats`` [rows, 2] fp32 (the folded-LayerNorm input of :func:`gemm`)."""
+    cols = int(cols if cols is not None else x.shape[-1])
+    rows = int(rows if rows is not None else x.numel() // cols)
+    assert stats.dtype == torch.float32
+    args = (x.data_ptr(), enum_of(x), int(ld if ld is not None else cols), rows, cols, float(eps), stats.data_ptr())
+    return Call(lib().distb200_row_stats, args, name, keep=(x, stats), nbytes=rows * cols * x.element_size())
 
 
 def attention(qkv, out, frames, tokens, heads, impl=IMPL_AUTO, name="attention"):

@@ -98,6 +98,13 @@ typedef struct distb200_gemm_desc {
     int64_t ld_out2;
     int32_t block_n;               /* tcgen05 N tile, 0 = choose */
     int32_t group_dim;             /* 2 (default when 0) or 3: which A coordinate the group index adds to */
+    /* LayerNorm folded into the GEMM: with A = the raw (un-normalised) rows x, B = W * gamma (per input column) and
+     * ln_stats[row] = (mean, rstd) of row gi*rows_per_group + r (distb200_row_stats), ln_wsum[n] = sum_k B[n][k],
+     * bias[n] = sum_k W[n][k] beta[k] + b[n], the epilogue computes  v = rstd * (acc - mean * ln_wsum[n]) + bias[n],
+     * which equals LayerNorm(x) W^T + b (clip.py:172-173 followed by in_proj / c_fc) without materialising LayerNorm(x).
+     * Both NULL = off.  Needs a bf16 `out` only (no out2 / res / taps). */
+    const float* ln_stats;
+    const float* ln_wsum;
 } distb200_gemm_desc;
 
 int distb200_gemm(const distb200_gemm_desc* desc, void* stream);
@@ -111,6 +118,10 @@ int distb200_layernorm(const float* in1, int64_t ld_in1, const float* in2, int64
                        const float* g1, const float* b1, void* y1, int64_t ld_y1,
                        const float* g2, const float* b2, void* y2, int64_t ld_y2,
                        int32_t out_dtype, void* stream);
+
+/* (mean, rstd) of every row of a [rows, cols] matrix (row pitch ld), biased variance + eps as LayerNorm uses them
+ * (clip.py:181-187): stats[2*row] = mean, stats[2*row + 1] = 1 / sqrt(var + eps).  Feeds distb200_gemm_desc.ln_stats. */
+int distb200_row_stats(const void* x, int32_t dtype, int64_t ld, int64_t rows, int32_t cols, float eps, float* stats, void* stream);
 
 /* Multi-head self attention over the N tokens of each frame, head dim 64, no mask
  * (nn.MultiheadAttention inside ResidualAttentionBlockMid, clip.py:155,166-168).

@@ -274,3 +274,32 @@ def test_patchify_u8_matches_to_tensor_normalize_patchify(p, dt):
         _run(ops.patchify(clip, want, b, T, R, R, p, first, step, n_sel, ld))
         _run(ops.patchify_u8(frames, got, b, T, R, R, p, first, step, n_sel, ld, mean, std))
         assert torch.equal(got, want)                                                             # same operation order: bit-exact
+
+
+@pytest.mark.parametrize("M,N,K,gelu", [(1000, 2304, 768, False), (777, 3072, 768, True), (300, 256, 1024, False), (130, 96, 128, True)])
+@pytest.mark.parametrize("impl", ["tcgen05", "simt"])
+def test_gemm_with_folded_layernorm(M, N, K, gelu, impl):
+    """LayerNorm(x) W^T + b computed as rstd * (x_bf16 (W*gamma)^T - mean * rowsum(W*gamma)) + (W beta + b): row_stats + GEMM epilogue."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(M + N)
+    x = (1.5 * torch.randn(M, K, generator=g) + 0.3).to(DEV)
+    x[:, 7] *= 20.0                                             # an outlier channel
+    W = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(DEV)
+    b = torch.randn(N, generator=g).to(DEV)
+    gamma, beta = (1 + 0.2 * torch.randn(K, generator=g)).to(DEV), (0.1 * torch.randn(K, generator=g)).to(DEV)
+    xb = x.to(torch.bfloat16)
+    wf = (W * gamma[None, :]).to(torch.bfloat16).contiguous()
+    wsum = wf.float().sum(dim=1).contiguous()
+    bias = (W.double() @ beta.double() + b.double()).float().contiguous()
+    stats = torch.empty(M, 2, device=DEV)
+    out = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+    _run(ops.row_stats(xb, stats))
+    _run(ops.gemm(xb, wf, N, K, bias=bias, out=out, ld_out=N, act=ops.ACT_QUICKGELU if gelu else ops.ACT_NONE, ln_stats=stats, ln_wsum=wsum,
+                  impl=ops.IMPL_SIMT if impl == "simt" else ops.IMPL_AUTO))
+    xd = xb.double()                                            # the statistics are those of the bf16 rows the GEMM reads
+    mu, var = xd.mean(dim=1, keepdim=True), xd.var(dim=1, unbiased=False, keepdim=True)
+    assert rel_l2(stats[:, 0], mu[:, 0]) < 1e-5 and rel_l2(stats[:, 1], (var[:, 0] + 1e-5).rsqrt()) < 1e-5
+    ref = ((xd - mu) / (var + 1e-5).sqrt() * gamma.double() + beta.double()) @ W.double().t() + b.double()
+    if gelu:
+        ref = _qgelu(ref)
+    assert rel_l2(out, ref) < 6e-3                              # bf16 weights (gamma folded) and bf16 output
