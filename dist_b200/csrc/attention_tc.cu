@@ -37,6 +37,7 @@ struct alignas(64) AttArgs {
     int tokens, heads, q_tiles;
     int keys_pad;                       // tokens rounded up to 16
     int slot_cols, o_col, n_slots;
+    int split_col;                      // S columns [0, split_col) are consumed before O (which aliases the S tail) may be written
     long long items;                    // frames * heads
 };
 
@@ -65,12 +66,12 @@ __device__ __forceinline__ float fast_exp2(float x) {
 }
 
 struct Bars {   // shared-memory addresses of the mbarriers
-    uint32_t kv_full, kv_empty, q_full, q_empty, s_full, p_full, o_full, slot_free;
+    uint32_t kv_full, kv_empty, q_full, q_empty, s_full, p_full, o_full, slot_free, p_early;
 };
 
 __global__ void __launch_bounds__(ATT_THREADS, 1) attention_tc_kernel(const __grid_constant__ AttArgs args) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t bar_mem[2 * KV_STAGES + 2 * Q_RING + 8];
+    __shared__ __align__(8) uint64_t bar_mem[2 * KV_STAGES + 2 * Q_RING + 10];
     __shared__ uint32_t tmem_slot;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -88,6 +89,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_tc_kernel(const __gr
     b.p_full = b.s_full + 16;
     b.o_full = b.p_full + 16;
     b.slot_free = b.o_full + 16;
+    b.p_early = b.slot_free + 16;
 
     if (warp == 9) {
         if (lane == 0) {
@@ -100,6 +102,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_tc_kernel(const __gr
                 ptx::mbar_init(b.p_full + 8 * i, 128);
                 ptx::mbar_init(b.o_full + 8 * i, 1);
                 ptx::mbar_init(b.slot_free + 8 * i, 128);
+                ptx::mbar_init(b.p_early + 8 * i, 128);
             }
             ptx::fence_barrier_init();
         }
@@ -153,9 +156,9 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_tc_kernel(const __gr
     } else if (warp == 9) {
         // ===================== S = Q K^T issuer =====================
         if (lane == 0) {
-            for (long long g = 0; g < total; ++g) {
-                const int it = (int)(g / QTn), qt = (int)(g % QTn);
-                const int st = it % KV_STAGES, qs = (int)(g % Q_RING), slot = (int)(g % ns);
+            for (uint32_t g = 0; g < (uint32_t)total; ++g) {
+                const int it = (int)(g / (uint32_t)QTn), qt = (int)(g % (uint32_t)QTn);
+                const int st = it % KV_STAGES, qs = (int)(g % Q_RING), slot = (int)(g % (uint32_t)ns);
                 if (qt == 0) ptx::mbar_wait(b.kv_full + 8 * st, (uint32_t)(it / KV_STAGES) & 1u);
                 ptx::mbar_wait(b.q_full + 8 * qs, (uint32_t)(g / Q_RING) & 1u);
                 ptx::mbar_wait(b.slot_free + 8 * slot, ((uint32_t)(g / ns) & 1u) ^ 1u);
@@ -179,14 +182,26 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_tc_kernel(const __gr
         if (lane == 0) {
             const uint32_t idesc_pv = ptx::umma_idesc_bf16(QT, HD) | (1u << 16);      // B (= V) is MN-major
             const int ksteps_pv = args.keys_pad / 16;
-            for (long long g = 0; g < total; ++g) {
-                const int it = (int)(g / QTn), qt = (int)(g % QTn);
-                const int st = it % KV_STAGES, slot = (int)(g % ns);
-                ptx::mbar_wait(b.p_full + 8 * slot, (uint32_t)(g / ns) & 1u);
-                ptx::tc_fence_after();
+            for (uint32_t g = 0; g < (uint32_t)total; ++g) {
+                const int it = (int)(g / (uint32_t)QTn), qt = (int)(g % (uint32_t)QTn);
+                const int st = it % KV_STAGES, slot = (int)(g % (uint32_t)ns);
+                // The probabilities arrive in two batches: p_early as soon as the softmax has read every S column that the O
+                // accumulator aliases (so that most of P V overlaps the remaining exponentials), p_full when the row is done.
+                const uint32_t ph = (uint32_t)(g / ns) & 1u;
                 const uint32_t sv = s_kv + (uint32_t)st * 2 * kv_bytes + kv_bytes;
                 const uint32_t ts = tmem + (uint32_t)(slot * args.slot_cols);
-                for (int ks = 0; ks < ksteps_pv; ++ks) {
+                const int ks_split = args.split_col < args.keys_pad ? args.split_col / 16 : 0;
+                if (ks_split > 0) {
+                    ptx::mbar_wait(b.p_early + 8 * slot, ph);
+                    ptx::tc_fence_after();
+                    for (int ks = 0; ks < ks_split; ++ks) {
+                        const uint64_t dv = ptx::umma_desc_k_sw128(sv + (uint32_t)ks * 16 * HD * 2);
+                        mma_f16_ts(ts + (uint32_t)args.o_col, ts + (uint32_t)(8 * ks), dv, idesc_pv, ks != 0);
+                    }
+                }
+                ptx::mbar_wait(b.p_full + 8 * slot, ph);
+                ptx::tc_fence_after();
+                for (int ks = ks_split; ks < ksteps_pv; ++ks) {
                     const uint64_t dv = ptx::umma_desc_k_sw128(sv + (uint32_t)ks * 16 * HD * 2);
                     mma_f16_ts(ts + (uint32_t)args.o_col, ts + (uint32_t)(8 * ks), dv, idesc_pv, ks != 0);
                 }
@@ -204,11 +219,14 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_tc_kernel(const __gr
             const int N = args.tokens;
             const int full_end = (N / 32) * 32;            // keys [0, full_end) need no validity predicate
             uint32_t use = 0;
-            for (long long g = grp; g < total; g += ns, ++use) {
-                const long long it = g / QTn;
-                const int qt = (int)(g - it * QTn);
-                const long long item = (long long)blockIdx.x + it * gridDim.x;
-                const int h = (int)(item % args.heads), f = (int)(item / args.heads);
+            // 32-bit index arithmetic (the host guarantees items * q_tiles < 2^31): 64-bit divisions cost ~10 % of a tile here
+            const uint32_t total32 = (uint32_t)total, qtn = (uint32_t)QTn, heads32 = (uint32_t)args.heads;
+            for (uint32_t g = (uint32_t)grp; g < total32; g += (uint32_t)ns, ++use) {
+                const uint32_t it = g / qtn;
+                const int qt = (int)(g - it * qtn);
+                const uint32_t item = blockIdx.x + it * gridDim.x;
+                const uint32_t f32i = item / heads32;
+                const int h = (int)(item - f32i * heads32), f = (int)f32i;
                 const uint32_t ph = use & 1u;
                 const int row = qt * QT + w4 * 32 + lane;
                 const bool warp_has_rows = qt * QT + w4 * 32 < N;
@@ -258,6 +276,11 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_tc_kernel(const __gr
                         }
                         // keys [c0, c0+32) -> 16 packed columns at c0/2: always behind the S read front of this lane
                         tmem_st16(ts + (uint32_t)(c0 >> 1), p);
+                        if (c0 + 32 == args.split_col && args.split_col < args.keys_pad) {      // first batch of P is complete
+                            ptx::tmem_st_wait();
+                            ptx::tc_fence_before();
+                            ptx::mbar_arrive(b.p_early + 8 * grp);
+                        }
                     }
                     if (full_end < args.keys_pad) {
                         uint32_t v[32];
@@ -280,6 +303,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_tc_kernel(const __gr
                     }
                     sum = s0 + s1;
                     ptx::tmem_st_wait();
+                } else if (args.split_col < args.keys_pad) {
+                    ptx::mbar_arrive(b.p_early + 8 * grp);             // a warp without rows still signs the early batch
                 }
                 ptx::tc_fence_before();
                 ptx::mbar_arrive(b.p_full + 8 * grp);
@@ -357,7 +382,10 @@ int attention_tc_launch(const void* qkv, void* out, int frames, int tokens, int 
     args.o_col = (keys_pad / 2 + 31) / 32 * 32;
     args.slot_cols = args.o_col + HD > keys_pad ? args.o_col + HD : keys_pad;
     args.n_slots = 2 * args.slot_cols <= 512 ? 2 : 1;
+    args.split_col = (args.o_col + HD + 31) / 32 * 32;       // first 32-column chunk boundary past the O region
+    if (args.split_col > tokens / 32 * 32 || args.o_col >= keys_pad) args.split_col = keys_pad;      // no chunk boundary there: one batch
     args.items = (long long)frames * heads;
+    DISTB200_REQUIRE(args.items * args.q_tiles < (1ll << 31), "attention(tcgen05): too many tiles");
     const int smem = Q_RING * (int)Q_TILE_BYTES + KV_STAGES * 2 * keys_pad * HD * 2 + 1024;
     static int smem_set = 0;
     if (smem > smem_set) {
