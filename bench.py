@@ -237,13 +237,34 @@ def run_train(args, arch, wl, world, rank, local, dev):
     clocks = sampler.stop() if rank == 0 else None
     value = world * b * args.steps / (total_ms / 1e3)
 
-    # end to end: pinned host clips + soft targets in, loss out, every step
+    # end to end: pinned host clips + soft targets in, loss out, every step.  The clips of step i+1 cross PCIe on a copy stream
+    # while step i computes (a pin_memory loader with .cuda(non_blocking=True), runs/train.py:87-89); every step's H2D copies
+    # and the D2H read of the loss are inside the timed region.
     host = [clips.clone().pin_memory(), clips.flip(0).clone().pin_memory()]
     host_t = target.clone().pin_memory()
     loss_host = torch.empty(1).pin_memory()
+    copy_stream = torch.cuda.Stream(dev)
+    dev_buf = [torch.empty_like(d_clips) for _ in range(2)]
+    dev_tgt = [torch.empty_like(d_target) for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+
+    def prefetch(i):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[i & 1])
+            dev_buf[i & 1].copy_(host[i & 1], non_blocking=True)
+            dev_tgt[i & 1].copy_(host_t, non_blocking=True)
+            ready[i & 1].record(copy_stream)
+
+    for ev in consumed:
+        ev.record(torch.cuda.current_stream())
+    prefetch(0)
 
     def e2e_step(i):
-        loss = eng.train_step(host[i & 1], host_t, lr)
+        prefetch(i + 1)
+        torch.cuda.current_stream().wait_event(ready[i & 1])
+        loss = eng.train_step(dev_buf[i & 1], dev_tgt[i & 1], lr)
+        consumed[i & 1].record(torch.cuda.current_stream())
         loss_host.copy_(loss, non_blocking=False)
 
     for i in range(2):
