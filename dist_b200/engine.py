@@ -244,6 +244,8 @@ class DistEngine:
 
         # ---- patch rows: sparse frames for the ViT (clip.py:271 restricted to the frames kept at :281-284),
         #      all frames for the temporal stem (dist.py:225)
+        self.sections = {"vit": [], "dist": []}
+        mark = len(self.calls)
         if self.input_format == "uint8":
             cut = lambda *args, **kw: ops.patchify_u8(*args, self.mean, self.std, **kw)
         else:
@@ -253,6 +255,8 @@ class DistEngine:
         if not shared:
             add(cut(self.video, self.patches_s, b, T, R, R, a.patch, 0, al, t, w.kp, name="patchify.sparse"))
 
+        self.sections["patchify"] = (mark, len(self.calls))
+        mark = len(self.calls)
         # ---- ViT embedding: conv1 as GEMM, + positional embedding, class row, ln_pre (clip.py:271-276)
         k1 = 3 * a.patch * a.patch
         src, fstride = (self.patches_d, al * P * w.kp) if shared else (self.patches_s, P * w.kp)
@@ -262,8 +266,11 @@ class DistEngine:
         add(ops.rows_bcast(self.h, N * D, F, D, w.cls_row, 1, False, name="vit.cls_rows"))   # class embedding + pos[0]
         self._ln(self.h, w.ln_pre, self.h, name="vit.ln_pre")
 
+        self.sections["embed"] = (mark, len(self.calls))
+        mark = len(self.calls)
         # ---- temporal stem: Conv3d(3->Ct,(kt,ps,ps)) = kt row-shifted GEMMs over patch rows (dist.py:178-181,225)
         self._plan_stem()
+        self.sections["stem"] = (mark, len(self.calls))
 
     def _stem_operand(self):
         """(a_dim, a_stride, taps) of the stem's A operand: the dense patch rows of a clip, kt row-shifted taps."""
@@ -293,13 +300,21 @@ class DistEngine:
         last_sel = sel[-1]
         for l in range(a.layers):
             want_tap = l in sel
+            mark = len(self.calls)
             self._plan_vit_layer(l, self.tap if (want_tap and bf) else None)
+            self.sections["vit"].append((mark, len(self.calls)))
             if want_tap:
+                mark = len(self.calls)
                 self._plan_dist_layer(sel.index(l))
+                self.sections["dist"].append((mark, len(self.calls)))
             if l == last_sel:
                 # mean over the sparse frames of the last tapped class token (dist.py:243)
+                mark = len(self.calls)
                 add(ops.mean_rows(self.h, N * D, t, b, D, self.clsmean, name="dist.cls_mean"))
+                self.sections["cls_mean"] = (mark, len(self.calls))
+        mark = len(self.calls)
         self._plan_head()
+        self.sections["head"] = (mark, len(self.calls))
 
     def _plan_vit_layer(self, l, tap_out):
         """ResidualAttentionBlockMid (clip.py:170-178); ``tap_out`` receives a copy of the block output (the tap).
@@ -437,6 +452,41 @@ class DistEngine:
         s = (stream or torch.cuda.current_stream(self.device)).cuda_stream
         for c in self.calls:
             c.launch(s)
+
+    def run_section(self, rng, stream=None):
+        s = (stream or torch.cuda.current_stream(self.device)).cuda_stream
+        for c in self.calls[rng[0]:rng[1]]:
+            c.launch(s)
+
+    def forward_vit(self, video):
+        """The frozen ViT alone (``VisionTransformer.forward``, clip.py:263-300): returns the fp32 residual stream after every
+        block, frame-major ``[b*t, N, D]`` (the reference's ``others["mid_feat"]["img"][l]`` is its ``[N, b*t, D]`` transpose)."""
+        a = self.arch
+        self.video.copy_(video, non_blocking=True)
+        for name in ("patchify", "embed"):
+            self.run_section(self.sections[name])
+        taps = []
+        for rng in self.sections["vit"]:
+            self.run_section(rng)
+            taps.append(self.h.view(self.batch * a.sparse_frames, a.tokens, a.width).clone())
+        return taps
+
+    def forward_dist(self, video, taps):
+        """The DiST side alone (``DiSTNetwork.forward``, dist.py:222-247) on externally supplied taps: ``taps[l]`` is the
+        frame-major ``[b*t, N, D]`` residual stream after ViT block ``l`` for every selected layer.  Returns ``[b, E]``."""
+        a = self.arch
+        self.video.copy_(video, non_blocking=True)
+        self.run_section(self.sections["patchify"])
+        self.run_section(self.sections["stem"])
+        sel = list(a.selected_layers)
+        for idx, l in enumerate(sel):
+            tap = taps[l].reshape(-1, a.width)
+            self.tap.copy_(tap)                                   # bf16 operand copy (fp32 path: the tap buffer is the stream itself)
+            self.run_section(self.sections["dist"][idx])
+        self.h.copy_(taps[sel[-1]].reshape(-1, a.width))           # the class-token mean reads the fp32 stream (dist.py:243)
+        self.run_section(self.sections["cls_mean"])
+        self.run_section(self.sections["head"])
+        return self.emb
 
     def capture(self):
         """Capture the plan into a CUDA graph (all buffers are static)."""

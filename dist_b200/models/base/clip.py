@@ -97,6 +97,42 @@ class VisionTransformer(nn.Module):
         self.transformer = Transformer(width, layers, heads, cfg=cfg)
         self.ln_post = LayerNorm(width)
         self.proj = nn.Parameter(scale * torch.randn(width, output_dim))
+        self._engines = {}
+
+    def forward(self, x, others=None):
+        """``VisionTransformer.forward`` of the reference (``clip.py:263-300``) as a stand-alone module: frames ``[b*T,3,H,W]``
+        -> ``(cls_x, x_logits, x[:, 1:], others)`` and, when ``others["mid_feat"]["img"]`` exists, the per-block taps
+        ``[N, b*t, D]`` (``clip.py:177``).  The blocks run on the CUDA path; ``ln_post`` / ``proj`` on the class tokens of the
+        kept frames (dead for DiST, ``clip.py:293-298``) are evaluated with the same kernels."""
+        from ... import ops
+        from ...engine import DistEngine
+        if not x.is_cuda:
+            raise RuntimeError("dist_b200 runs on a CUDA device only; there is no CPU path")
+        bt, c, hh, ww = x.shape
+        T = self.num_frames
+        b = bt // T
+        arch = arch_from_cfg(self.cfg, {"visual." + k: v for k, v in self.state_dict().items()})
+        key = (b, str(x.device), sum(p._version for p in self.parameters()))
+        if key not in self._engines:
+            self._engines.clear()
+            sd = synth.synth_state_dict(arch, seed=0)              # the DiST half is never run here; any weights will do
+            sd.update({"visual." + k: v.detach() for k, v in self.state_dict().items()})
+            b200 = getattr(self.cfg, "B200", None)
+            self._engines[key] = DistEngine(sd, arch, b, device=x.device, precision=getattr(b200, "PRECISION", "bf16") if b200 else "bf16")
+        eng = self._engines[key]
+        taps = eng.forward_vit(x.view(b, T, c, hh, ww).permute(0, 2, 1, 3, 4).float().contiguous())
+        if others is not None and "mid_feat" in others and "img" in others["mid_feat"]:
+            for l, tp in enumerate(taps):
+                others["mid_feat"]["img"][l] = tp.permute(1, 0, 2).contiguous()
+        last = taps[-1]                                                                  # [b*t, N, D]
+        cls = last[:, 0].contiguous()
+        x_logits = torch.empty_like(cls)
+        st = torch.cuda.current_stream(x.device).cuda_stream
+        ops.layernorm(cls, self.ln_post.weight.detach().float(), self.ln_post.bias.detach().float(), x_logits).launch(st)
+        pw = self.proj.detach().float().t().contiguous()                               # [E, D]
+        cls_x = torch.empty(cls.shape[0], pw.shape[0], device=x.device)
+        ops.gemm(x_logits, pw, pw.shape[0], pw.shape[1], out=cls_x, ld_out=pw.shape[0]).launch(st)
+        return cls_x, x_logits, last[:, 1:, :], others
 
 
 class CLIP(nn.Module):

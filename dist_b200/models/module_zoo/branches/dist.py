@@ -128,3 +128,37 @@ class DiSTNetwork(nn.Module):
         self.proj = nn.Parameter((ci ** -0.5) * torch.randn(ci, output_dim))
         self.aggregated_cls_token = nn.Parameter(torch.zeros((1, 1, ci)))
         self.aggregated_spatial_cls_token = nn.Parameter(torch.zeros((1, 1, ci)))
+        self._d_model, self._output_dim = d_model, output_dim
+        self._engines = {}
+
+    def forward(self, input):
+        """``DiSTNetwork.forward`` of the reference (``dist.py:222-247``) as a stand-alone module: reads the taps
+        ``input["mid_feat"]["img"][layer_id]`` (``[N, b*t, D]``, frame index ``b*t + ti``) of the selected layers and the frames
+        ``input["images"]`` (``[b*T, 3, H, W]``); returns ``(cls_x [b, E], input)``."""
+        from ....arch import arch_from_cfg
+        from ....engine import DistEngine
+        from ....utils import synth
+        images = input["images"]
+        if not images.is_cuda:
+            raise RuntimeError("dist_b200 runs on a CUDA device only; there is no CPU path")
+        taps_in = input["mid_feat"]["img"]
+        n_tok, bt, c = taps_in[self.selected_layers[0]].shape
+        t = self.num_frames // self.alpha
+        b = bt // t
+        key = (b, str(images.device), sum(p._version for p in self.parameters()))
+        if key not in self._engines:
+            self._engines.clear()
+            own = {"dist_net." + k: v.detach() for k, v in self.state_dict().items()}
+            arch = arch_from_cfg(self.cfg)
+            arch.width, arch.embed_dim = self._d_model, self._output_dim
+            arch.validate()
+            sd = synth.synth_state_dict(arch, seed=0)              # the ViT half is never run here; any weights will do
+            sd.update(own)
+            b200 = getattr(self.cfg, "B200", None)
+            self._engines[key] = DistEngine(sd, arch, b, device=images.device, precision=getattr(b200, "PRECISION", "bf16") if b200 else "bf16")
+        eng = self._engines[key]
+        hh, ww = images.shape[-2:]
+        video = images.view(b, self.num_frames, 3, hh, ww).permute(0, 2, 1, 3, 4).float().contiguous()
+        taps = {l: taps_in[l].permute(1, 0, 2).contiguous().float() for l in self.selected_layers}
+        cls_x = eng.forward_dist(video, taps).clone()
+        return cls_x, input

@@ -215,3 +215,34 @@ def test_perform_test_multi_view_loop():
     assert bool((meter.clip_count == K).all())
     top1 = float((want.argmax(dim=1) == labels).float().mean()) * 100
     assert stats["top1_acc"] == "{:.2f}".format(top1)
+
+
+def test_stand_alone_vit_and_dist_modules():
+    """The module-level surface of the reference: VisionTransformer.forward fills others["mid_feat"]["img"][l] (clip.py:263-300,177)
+    and DiSTNetwork.forward(others) consumes those taps plus others["images"] (dist.py:222-247) - each on its own, against
+    the fixture the reference produced (B/16 8+16f)."""
+    import os
+    from conftest import ROOT
+    import dist_b200.models.base  # noqa: F401
+    from dist_b200.config import Config
+    from dist_b200.models.base.builder import build_model
+    fix = load_golden("b16_8x16_ref")
+    arch, sd, clips, text = inputs_for(fix)
+    cfg = Config.from_file(os.path.join(ROOT, "configs/projects/dist/ssv2/vit-b16-8+16f.yaml"), ["NUM_GPUS", "1"])
+    model, _ = build_model(cfg)
+    enc = model.backbone.base_encoder
+    enc.load_state_dict(sd, strict=True)
+    frames = clips.permute(0, 2, 1, 3, 4).reshape(-1, 3, 224, 224).cuda()                  # backbone.py:233
+    others = {"mid_feat": {"img": {}}}
+    cls_x, x_logits, patches, others = enc.visual(frames, others)
+    b, t = 2, arch.sparse_frames
+    assert cls_x.shape == (b * t, arch.embed_dim) and patches.shape == (b * t, arch.patches, arch.width)
+    rs, cs = fix["sample_stride"]
+    for l in range(arch.layers):
+        tap = others["mid_feat"]["img"][l]                                                   # [N, b*t, D]
+        assert tap.shape == (arch.tokens, b * t, arch.width)
+        ref = fix["parts"]["tap.%d" % l]                                                     # frame-major, sub-sampled
+        assert rel_l2(tap.permute(1, 0, 2)[..., ::rs, ::cs], ref) < 2e-2, l
+    others["images"] = frames
+    emb, others = enc.dist_net(others)
+    assert emb.shape == (b, arch.embed_dim) and rel_l2(emb, fix["emb"]) < BF16_BAR
