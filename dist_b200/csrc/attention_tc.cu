@@ -13,6 +13,7 @@
 // With 257 tokens a slot needs 272 columns and only one fits the 512-column TMEM: group 1 idles and the S MMA,
 // softmax and PV MMA of a tile run back to back (the loads still run ahead).
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "ptx.cuh"
@@ -35,7 +36,9 @@ struct alignas(64) AttArgs {
     CUtensorMap tm16;                   // same tensor, box (64, 16, 1) for the ragged tail of K / V
     bf16* out;
     int tokens, heads, q_tiles;
-    int keys_pad;                       // tokens rounded up to 16
+    int keys_pad;                       // keys on the tensor-core path (multiple of 16)
+    int keys_ld;                        // K / V rows held in shared memory (tokens rounded up to 16)
+    int odd;                            // 1: the last key (index keys_pad) is handled on the CUDA cores, see below
     int slot_cols, o_col, n_slots;
     int split_col;                      // S columns [0, split_col) are consumed before O (which aliases the S tail) may be written
     long long items;                    // frames * heads
@@ -76,7 +79,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_tc_kernel(const __gr
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int D = args.heads * HD;
-    const uint32_t kv_bytes = (uint32_t)args.keys_pad * HD * 2;          // one of K / V
+    const uint32_t kv_bytes = (uint32_t)args.keys_ld * HD * 2;           // one of K / V
     const uint32_t s_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t s_q = s_base;                                          // Q_RING tiles
     const uint32_t s_kv = s_q + Q_RING * Q_TILE_BYTES;                    // KV_STAGES x (K | V)
@@ -95,8 +98,10 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_tc_kernel(const __gr
         if (lane == 0) {
             ptx::prefetch_tensormap(&args.tm64);
             ptx::prefetch_tensormap(&args.tm16);
-            for (int i = 0; i < KV_STAGES; ++i) { ptx::mbar_init(b.kv_full + 8 * i, 1); ptx::mbar_init(b.kv_empty + 8 * i, 1); }
-            for (int i = 0; i < Q_RING; ++i) { ptx::mbar_init(b.q_full + 8 * i, 1); ptx::mbar_init(b.q_empty + 8 * i, 1); }
+            // odd-key mode: the epilogue of an item's last tile still reads the odd V row, so its 128 threads co-sign the release of K / V
+            for (int i = 0; i < KV_STAGES; ++i) { ptx::mbar_init(b.kv_full + 8 * i, 1); ptx::mbar_init(b.kv_empty + 8 * i, args.odd ? 129 : 1); }
+            // odd-key mode: the softmax threads read their Q row from shared memory, so they co-sign the release of a Q tile
+            for (int i = 0; i < Q_RING; ++i) { ptx::mbar_init(b.q_full + 8 * i, 1); ptx::mbar_init(b.q_empty + 8 * i, args.odd ? 129 : 1); }
             for (int i = 0; i < 2; ++i) {
                 ptx::mbar_init(b.s_full + 8 * i, 1);
                 ptx::mbar_init(b.p_full + 8 * i, 128);
@@ -124,7 +129,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_tc_kernel(const __gr
     if (warp == 8) {
         // ===================== TMA producer =====================
         if (lane == 0) {
-            const int boxes64 = args.keys_pad / 64, tail16 = (args.keys_pad % 64) / 16;
+            const int boxes64 = args.keys_ld / 64, tail16 = (args.keys_ld % 64) / 16;
             long long g = 0;
             int it = 0;
             for (long long item = blockIdx.x; item < args.items; item += gridDim.x, ++it) {
@@ -216,7 +221,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_tc_kernel(const __gr
         if (grp < ns) {
             const uint32_t ts = tmem + ((uint32_t)(w4 * 32) << 16) + (uint32_t)(grp * args.slot_cols);
             const float c = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e)
-            const int N = args.tokens;
+            const int N = args.tokens - args.odd;          // keys on the tensor-core path
+            const int NR = args.tokens;                    // query rows
             const int full_end = (N / 32) * 32;            // keys [0, full_end) need no validity predicate
             uint32_t use = 0;
             // 32-bit index arithmetic (the host guarantees items * q_tiles < 2^31): 64-bit divisions cost ~10 % of a tile here
@@ -229,13 +235,38 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_tc_kernel(const __gr
                 const int h = (int)(item - f32i * heads32), f = (int)f32i;
                 const uint32_t ph = use & 1u;
                 const int row = qt * QT + w4 * 32 + lane;
-                const bool warp_has_rows = qt * QT + w4 * 32 < N;
+                const bool warp_has_rows = qt * QT + w4 * 32 < NR;
                 ptx::mbar_wait(b.s_full + 8 * grp, ph);
                 ptx::tc_fence_after();
                 float sum = 0.f;
+                float s_x = -INFINITY, p_x = 0.f;
+                if (args.odd) {
+                    // The last key does not fit the TMEM budget of two slots (257 keys -> 272 fp32 columns): its score is one
+                    // 64-term dot product per row on the CUDA cores, straight from the swizzled Q / K tiles in shared memory.
+                    if (warp_has_rows) {
+                        const int st = (int)(it % KV_STAGES), qs = (int)(g % Q_RING);
+                        const int r = w4 * 32 + lane;
+                        const uint4* qrow = reinterpret_cast<const uint4*>(smem_raw + (s_q - ptx::smem_u32(smem_raw)) + qs * Q_TILE_BYTES + r * 128);
+                        const uint4* krow = reinterpret_cast<const uint4*>(smem_raw + (s_kv - ptx::smem_u32(smem_raw)) + (uint32_t)st * 2 * kv_bytes +
+                                                                           (uint32_t)args.keys_pad * 128);
+                        float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const uint4 qa = qrow[j ^ (r & 7)], ka = krow[j];          // row keys_pad is a multiple of 8: not swizzled
+                            const uint32_t qw[4] = {qa.x, qa.y, qa.z, qa.w}, kw[4] = {ka.x, ka.y, ka.z, ka.w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                acc0 = fmaf(__uint_as_float(qw[e] << 16), __uint_as_float(kw[e] << 16), acc0);
+                                acc1 = fmaf(__uint_as_float(qw[e] & 0xffff0000u), __uint_as_float(kw[e] & 0xffff0000u), acc1);
+                            }
+                        }
+                        s_x = acc0 + acc1;
+                    }
+                    ptx::mbar_arrive(b.q_empty + 8 * (uint32_t)(g % Q_RING));
+                }
                 if (warp_has_rows) {
                     // pass 1: row maximum over the valid keys
-                    float mx = -INFINITY;
+                    float mx = s_x;
                     for (int c0 = 0; c0 < full_end; c0 += 32) {
                         uint32_t v[32];
                         ptx::tmem_ld32(ts + (uint32_t)c0, v);
@@ -301,7 +332,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_tc_kernel(const __gr
                         }
                         tmem_st16(ts + (uint32_t)(full_end >> 1), p);
                     }
-                    sum = s0 + s1;
+                    if (args.odd) p_x = fast_exp2(fmaf(s_x, c, -mxs));
+                    sum = s0 + s1 + p_x;
                     ptx::tmem_st_wait();
                 } else if (args.split_col < args.keys_pad) {
                     ptx::mbar_arrive(b.p_early + 8 * grp);             // a warp without rows still signs the early batch
@@ -312,13 +344,28 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_tc_kernel(const __gr
                 ptx::tc_fence_after();
                 if (warp_has_rows) {
                     const float inv = 1.f / sum;
-                    bf16* dst_row = args.out + ((long long)f * N + row) * D + h * HD;
+                    bf16* dst_row = args.out + ((long long)f * NR + row) * D + h * HD;
 #pragma unroll
                     for (int half = 0; half < 2; ++half) {
                         uint32_t o[32];
                         ptx::tmem_ld32(ts + (uint32_t)args.o_col + 32u * half, o);
                         ptx::tmem_ld_wait();
-                        if (row < N) {
+                        if (args.odd) {
+                            const int st = (int)(it % KV_STAGES);
+                            const uint4* vrow = reinterpret_cast<const uint4*>(smem_raw + (s_kv - ptx::smem_u32(smem_raw)) + (uint32_t)st * 2 * kv_bytes +
+                                                                               kv_bytes + (uint32_t)args.keys_pad * 128) + 4 * half;
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const uint4 va = vrow[j];
+                                const uint32_t vw[4] = {va.x, va.y, va.z, va.w};
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    o[8 * j + 2 * e] = __float_as_uint(fmaf(p_x, __uint_as_float(vw[e] << 16), __uint_as_float(o[8 * j + 2 * e])));
+                                    o[8 * j + 2 * e + 1] = __float_as_uint(fmaf(p_x, __uint_as_float(vw[e] & 0xffff0000u), __uint_as_float(o[8 * j + 2 * e + 1])));
+                                }
+                            }
+                        }
+                        if (row < NR) {
                             uint4* dst = reinterpret_cast<uint4*>(dst_row + 32 * half);
 #pragma unroll
                             for (int i = 0; i < 4; ++i)
@@ -329,6 +376,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_tc_kernel(const __gr
                         }
                     }
                 }
+                if (args.odd && qt == (int)qtn - 1) ptx::mbar_arrive(b.kv_empty + 8 * (uint32_t)(it % KV_STAGES));
                 ptx::tc_fence_before();
                 ptx::mbar_arrive(b.slot_free + 8 * grp);
             }
@@ -349,7 +397,8 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 }  // namespace
 
 int attention_tc_launch(const void* qkv, void* out, int frames, int tokens, int heads, cudaStream_t stream) {
-    const int keys_pad = (tokens + 15) / 16 * 16;
+    int keys_pad = (tokens + 15) / 16 * 16;
+    const int keys_ld = keys_pad;
     if (keys_pad > 288 || ((uintptr_t)qkv & 15) || ((uintptr_t)out & 15))
         return attention_simt_launch(qkv, out, frames, tokens, heads, DISTB200_BF16, stream);
 
@@ -378,15 +427,28 @@ int attention_tc_launch(const void* qkv, void* out, int frames, int tokens, int 
     args.tokens = tokens;
     args.heads = heads;
     args.q_tiles = (tokens + QT - 1) / QT;
+    // 257 tokens (ViT-L/14): 272 fp32 score columns per slot would leave room for ONE slot in the 512-column TMEM and
+    // serialise S-MMA -> softmax -> PV-MMA -> epilogue.  With the single odd key taken off the tensor core, two slots of 256 fit.
+    args.odd = 0;
+    {
+        const int oc = (keys_pad / 2 + 31) / 32 * 32, sc = oc + HD > keys_pad ? oc + HD : keys_pad;
+        const int kp2 = keys_pad - 16, oc2 = (kp2 / 2 + 31) / 32 * 32, sc2 = oc2 + HD > kp2 ? oc2 + HD : kp2;
+        static const int odd_env = getenv("DISTB200_ATT_ODD") ? atoi(getenv("DISTB200_ATT_ODD")) : 1;
+        if (odd_env && tokens % 16 == 1 && kp2 >= 32 && 2 * sc > 512 && 2 * sc2 <= 512) {
+            args.odd = 1;
+            keys_pad = kp2;
+        }
+    }
+    args.keys_ld = keys_ld;
     args.keys_pad = keys_pad;
     args.o_col = (keys_pad / 2 + 31) / 32 * 32;
     args.slot_cols = args.o_col + HD > keys_pad ? args.o_col + HD : keys_pad;
     args.n_slots = 2 * args.slot_cols <= 512 ? 2 : 1;
     args.split_col = (args.o_col + HD + 31) / 32 * 32;       // first 32-column chunk boundary past the O region
-    if (args.split_col > tokens / 32 * 32 || args.o_col >= keys_pad) args.split_col = keys_pad;      // no chunk boundary there: one batch
+    if (args.split_col > (tokens - args.odd) / 32 * 32 || args.o_col >= keys_pad) args.split_col = keys_pad;      // no chunk boundary there: one batch
     args.items = (long long)frames * heads;
     DISTB200_REQUIRE(args.items * args.q_tiles < (1ll << 31), "attention(tcgen05): too many tiles");
-    const int smem = Q_RING * (int)Q_TILE_BYTES + KV_STAGES * 2 * keys_pad * HD * 2 + 1024;
+    const int smem = Q_RING * (int)Q_TILE_BYTES + KV_STAGES * 2 * keys_ld * HD * 2 + 1024;
     static int smem_set = 0;
     if (smem > smem_set) {
         cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
