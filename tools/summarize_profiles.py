@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 G = os.path.join(ROOT, "gpurun_out")
 P = os.path.join(ROOT, "profiles")
 
-LAYER0 = ["vit.ln_1", "vit.qkv", "vit.attention", "vit.out_proj", "vit.ln_2", "vit.fc1", "vit.fc2", "dist.tn.ln", "dist.tn.conv_t",
+LAYER0 = ["vit.ln_1", "vit.qkv", "vit.attention", "vit.out_proj", "vit.ln_2.stats", "vit.fc1", "vit.fc2", "dist.tn.ln", "dist.tn.conv_t",
           "dist.tn.conv_s", "dist.input_linear", "dist.t2i", "dist.t2i.cls", "dist.i2t", "dist.int.ln", "dist.int.ffn_fc",
           "dist.int.t_fc1", "dist.int.t_conv", "dist.int.proj"]
 METRICS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
