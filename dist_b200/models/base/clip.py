@@ -67,6 +67,45 @@ class ResidualAttentionBlockMid(nn.Module):
         self.ln_2 = LayerNorm(d_model)
         self.attn_mask = None
         self.is_image_transformer = True
+        self._packed = None
+
+    def forward(self, xo):
+        """Block protocol of the reference (``clip.py:170-178``): ``(x [N, b*t, D], others) -> (x, others)`` with
+        ``x += MHA(ln_1 x)``, ``x += mlp(ln_2 x)`` and the tap ``others["mid_feat"]["img"][layer_id] = x.clone()``.
+        Stand-alone (eager) use of the same kernels the planned engine launches; fp32 residual stream, bf16 operands."""
+        from ... import ops
+        x, others = xo
+        if not x.is_cuda:
+            raise RuntimeError("dist_b200 runs on a CUDA device only; there is no CPU path")
+        n_tok, bt, d = x.shape
+        heads = self.attn.num_heads
+        version = sum(p._version for p in self.parameters())
+        if self._packed is None or self._packed[0] != version or self._packed[1] != x.device:
+            bf = lambda t: t.detach().to(device=x.device, dtype=torch.bfloat16).contiguous()
+            f32 = lambda t: t.detach().to(device=x.device, dtype=torch.float32).contiguous()
+            self._packed = (version, x.device, dict(
+                qkv_w=bf(self.attn.in_proj_weight), qkv_b=f32(self.attn.in_proj_bias), proj_w=bf(self.attn.out_proj.weight),
+                proj_b=f32(self.attn.out_proj.bias), fc1_w=bf(self.mlp.c_fc.weight), fc1_b=f32(self.mlp.c_fc.bias),
+                fc2_w=bf(self.mlp.c_proj.weight), fc2_b=f32(self.mlp.c_proj.bias),
+                ln1=(f32(self.ln_1.weight), f32(self.ln_1.bias)), ln2=(f32(self.ln_2.weight), f32(self.ln_2.bias))))
+        w = self._packed[2]
+        st = torch.cuda.current_stream(x.device).cuda_stream
+        h = x.detach().float().permute(1, 0, 2).reshape(bt * n_tok, d).contiguous()          # frame-major rows
+        rows = h.shape[0]
+        z = lambda *shape, dtype=torch.bfloat16: torch.empty(*shape, device=x.device, dtype=dtype)
+        ln_buf, qkv, att, fc1 = z(rows, d), z(rows, 3 * d), z(rows, d), z(rows, 4 * d)
+        lin = lambda a, wt, b, out, **kw: ops.gemm(a, wt, wt.shape[0], wt.shape[1], bias=b, out=out, ld_out=wt.shape[0], ld_res=wt.shape[0], **kw).launch(st)
+        ops.layernorm(h, w["ln1"][0], w["ln1"][1], ln_buf).launch(st)
+        lin(ln_buf, w["qkv_w"], w["qkv_b"], qkv)
+        ops.attention(qkv, att, bt, n_tok, heads).launch(st)
+        lin(att, w["proj_w"], w["proj_b"], h, res=h)
+        ops.layernorm(h, w["ln2"][0], w["ln2"][1], ln_buf).launch(st)
+        lin(ln_buf, w["fc1_w"], w["fc1_b"], fc1, act=ops.ACT_QUICKGELU)
+        lin(fc1, w["fc2_w"], w["fc2_b"], h, res=h)
+        out = h.view(bt, n_tok, d).permute(1, 0, 2).contiguous()
+        if others is not None and "mid_feat" in others and "img" in others["mid_feat"]:
+            others["mid_feat"]["img"][self.layer_id] = out.clone()                           # clip.py:177
+        return out, others
 
 
 class Transformer(nn.Module):

@@ -246,3 +246,27 @@ def test_stand_alone_vit_and_dist_modules():
     others["images"] = frames
     emb, others = enc.dist_net(others)
     assert emb.shape == (b, arch.embed_dim) and rel_l2(emb, fix["emb"]) < BF16_BAR
+
+
+def test_stand_alone_attention_block_protocol():
+    """ATTEN_BLOCK_REGISTRY["ResidualAttentionBlockMid"](d_model, n_head, None, cfg=, layer_id=).forward((x, others)) writes the tap
+    and matches the restated block (clip.py:170-178) on the fixture's weights."""
+    from dist_b200.models.base.clip import ATTEN_BLOCK_REGISTRY
+    from oracle import dist_oracle
+    fix = load_golden("tiny_scaled")
+    arch, sd, _, _ = inputs_for(fix)
+    blk = ATTEN_BLOCK_REGISTRY.get("ResidualAttentionBlockMid")(arch.width, arch.heads, None, cfg=None, layer_id=1)
+    pre = "visual.transformer.resblocks.1."
+    blk.load_state_dict({k[len(pre):]: v for k, v in sd.items() if k.startswith(pre)}, strict=True)
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(arch.tokens, 6, arch.width, generator=g)                                  # [N, b*t, D]
+    others = {"mid_feat": {"img": {}}}
+    y, others = blk.cuda()((x.cuda(), others))
+    sd64 = {k: v.double() for k, v in sd.items()}
+    h = x.double().permute(1, 0, 2)
+    t = dist_oracle._ln(h, sd64[pre + "ln_1.weight"], sd64[pre + "ln_1.bias"])
+    h = h + dist_oracle._mha(t, t, sd64, pre[:-1] + ".attn", arch.heads)
+    t = dist_oracle._ln(h, sd64[pre + "ln_2.weight"], sd64[pre + "ln_2.bias"])
+    h = h + dist_oracle._lin(dist_oracle._qgelu(dist_oracle._lin(t, sd64, pre + "mlp.c_fc")), sd64, pre + "mlp.c_proj")
+    assert y.shape == x.shape and rel_l2(y.permute(1, 0, 2), h) < 1e-2
+    assert torch.equal(others["mid_feat"]["img"][1], y)
