@@ -45,6 +45,7 @@ struct alignas(64) TcArgs {
     int block_n;
     int stages;
     int k_blocks;
+    int kpack;                // 64-wide k-blocks per pipeline stage: 2 when 64 < K <= 128 (one stage per tap: half the barrier round trips)
     int rows_per_tile;
     int tiles_per_group;
     int n_tiles;
@@ -334,7 +335,8 @@ __global__ void __launch_bounds__(num_threads(EW), 1) gemm_tcgen05_kernel(const 
     // carve shared memory: [stages x (A | B)] [epilogue staging] [barriers]; swizzle-128B needs 1024-byte aligned
     // stage bases.  Both CTAs of a pair use the same offsets (the pair MMA addresses the peer's operands by offset).
     const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t stage_bytes = A_STAGE_BYTES + args.b_stage_bytes;
+    const uint32_t sub_bytes = A_STAGE_BYTES + args.b_stage_bytes;            // one 64-wide k-block of A and B
+    const uint32_t stage_bytes = sub_bytes * (uint32_t)args.kpack;
     const uint32_t staging_base = smem_base + (uint32_t)args.stages * stage_bytes;
     const uint32_t bar_base = staging_base + staging_bytes(EW);
     // barriers (8 bytes each): full[MAX_STAGES], empty[MAX_STAGES], tmem_full[2], tmem_empty[2], then the TMEM base
@@ -373,7 +375,7 @@ __global__ void __launch_bounds__(num_threads(EW), 1) gemm_tcgen05_kernel(const 
     const uint32_t tmem_base = *tmem_slot_ptr;
     grid_dep_sync();          // PDL: everything above overlapped the previous kernel's tail; global memory is touched below
 
-    const int iters = PROBE(32) ? 1 : d.num_taps * args.k_blocks;
+    const int iters = PROBE(32) ? 1 : d.num_taps * (args.k_blocks / args.kpack);
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -397,19 +399,21 @@ __global__ void __launch_bounds__(num_threads(EW), 1) gemm_tcgen05_kernel(const 
                         c2 = d.tap_off[tap][1] + (args.group_dim == 3 ? 0 : (int)tc.gi);
                         c3 = d.tap_off[tap][2] + (args.group_dim == 3 ? (int)tc.gi : 0);
                     }
-                    for (int kb = 0; kb < (PROBE(32) ? 1 : args.k_blocks); ++kb) {
+                    for (int kb0 = 0; kb0 < (PROBE(32) ? 1 : args.k_blocks); kb0 += args.kpack) {
                         ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
-                        const uint32_t sa = smem_base + (uint32_t)stage * stage_bytes;
-                        const uint32_t sb = sa + A_STAGE_BYTES;
+                        const uint32_t s0 = smem_base + (uint32_t)stage * stage_bytes;
                         if (CTAS == 2) {
                             // All bytes of the pair are counted on the leader's barrier, where the MMA issuer waits.  The peer
                             // needs no arrive of its own: it can only refill a stage after the leader's MMAs released it
                             // (multicast commit below), i.e. after the barrier's previous phase completed.
                             const uint32_t lead_full = ptx::mapa(full_bar(stage), 0);
                             if (ptx::elect_one()) {
-                                if (rank == 0) ptx::mbar_arrive_expect_tx(full_bar(stage), 2 * args.tx_bytes);
-                                ptx::tma_load_4d_2sm(sa, &args.tm_a, lead_full, kb * BLOCK_K, c1, c2, c3);
-                                ptx::tma_load_3d_2sm(sb, &args.tm_b, lead_full, kb * BLOCK_K, tc.n0 + rank * b_rows, tap);
+                                if (rank == 0) ptx::mbar_arrive_expect_tx(full_bar(stage), 2 * args.tx_bytes * (uint32_t)args.kpack);
+                                for (int j = 0; j < args.kpack; ++j) {
+                                    const uint32_t sa = s0 + (uint32_t)j * sub_bytes, sb = sa + A_STAGE_BYTES;
+                                    ptx::tma_load_4d_2sm(sa, &args.tm_a, lead_full, (kb0 + j) * BLOCK_K, c1, c2, c3);
+                                    ptx::tma_load_3d_2sm(sb, &args.tm_b, lead_full, (kb0 + j) * BLOCK_K, tc.n0 + rank * b_rows, tap);
+                                }
                             }
                         } else if (ptx::elect_one()) {
 #ifdef DISTB200_GEMM_PROBES
@@ -417,13 +421,20 @@ __global__ void __launch_bounds__(num_threads(EW), 1) gemm_tcgen05_kernel(const 
                             const uint32_t b_bytes = (uint32_t)(BLOCK_K * args.block_n * 2);
                             if (PROBE(4)) tx -= args.tx_bytes - b_bytes;
                             if (PROBE(8)) tx -= b_bytes;
+                            tx *= (uint32_t)args.kpack;
                             if (tx) ptx::mbar_arrive_expect_tx(full_bar(stage), tx); else ptx::mbar_arrive(full_bar(stage));
-                            if (!PROBE(4)) ptx::tma_load_4d(sa, &args.tm_a, full_bar(stage), kb * BLOCK_K, c1, c2, c3);
-                            if (!PROBE(8)) ptx::tma_load_3d(sb, &args.tm_b, full_bar(stage), kb * BLOCK_K, tc.n0, tap);
+                            for (int j = 0; j < args.kpack; ++j) {
+                                const uint32_t sa = s0 + (uint32_t)j * sub_bytes, sb = sa + A_STAGE_BYTES;
+                                if (!PROBE(4)) ptx::tma_load_4d(sa, &args.tm_a, full_bar(stage), (kb0 + j) * BLOCK_K, c1, c2, c3);
+                                if (!PROBE(8)) ptx::tma_load_3d(sb, &args.tm_b, full_bar(stage), (kb0 + j) * BLOCK_K, tc.n0, tap);
+                            }
 #else
-                            ptx::mbar_arrive_expect_tx(full_bar(stage), args.tx_bytes);
-                            ptx::tma_load_4d(sa, &args.tm_a, full_bar(stage), kb * BLOCK_K, c1, c2, c3);
-                            ptx::tma_load_3d(sb, &args.tm_b, full_bar(stage), kb * BLOCK_K, tc.n0, tap);
+                            ptx::mbar_arrive_expect_tx(full_bar(stage), args.tx_bytes * (uint32_t)args.kpack);
+                            for (int j = 0; j < args.kpack; ++j) {
+                                const uint32_t sa = s0 + (uint32_t)j * sub_bytes, sb = sa + A_STAGE_BYTES;
+                                ptx::tma_load_4d(sa, &args.tm_a, full_bar(stage), (kb0 + j) * BLOCK_K, c1, c2, c3);
+                                ptx::tma_load_3d(sb, &args.tm_b, full_bar(stage), (kb0 + j) * BLOCK_K, tc.n0, tap);
+                            }
 #endif
                         }
                         __syncwarp();
@@ -451,21 +462,24 @@ __global__ void __launch_bounds__(num_threads(EW), 1) gemm_tcgen05_kernel(const 
                 for (int it = 0; it < iters; ++it) {
                     ptx::mbar_wait(full_bar(stage), phase);
                     ptx::tc_fence_after();
-                    const uint64_t da = desc0 + (uint64_t)(((uint32_t)stage * stage_bytes) >> 4);
-                    const uint64_t db = da + (uint64_t)(A_STAGE_BYTES >> 4);
-                    const int ksteps = kb == args.k_blocks - 1 ? ksteps_last : BLOCK_K / 16;
                     if (ptx::elect_one()) {
-                        for (int ks = 0; ks < (PROBE(2) ? 0 : ksteps); ++ks) {
-                            // advancing 16 bf16 (32 bytes) along K inside the swizzle row: +2 in the (addr >> 4) field
-                            if (CTAS == 2) ptx::mma_f16_ss_2sm(tmem_d, da + (uint64_t)(2 * ks), db + (uint64_t)(2 * ks), idesc, (it | ks) != 0);
-                            else ptx::mma_f16_ss(tmem_d, da + (uint64_t)(2 * ks), db + (uint64_t)(2 * ks), idesc, (it | ks) != 0);
+                        for (int j = 0; j < args.kpack; ++j) {
+                            const uint64_t da = desc0 + (uint64_t)(((uint32_t)stage * stage_bytes + (uint32_t)j * sub_bytes) >> 4);
+                            const uint64_t db = da + (uint64_t)(A_STAGE_BYTES >> 4);
+                            const int ksteps = kb + j == args.k_blocks - 1 ? ksteps_last : BLOCK_K / 16;
+                            for (int ks = 0; ks < (PROBE(2) ? 0 : ksteps); ++ks) {
+                                // advancing 16 bf16 (32 bytes) along K inside the swizzle row: +2 in the (addr >> 4) field
+                                if (CTAS == 2) ptx::mma_f16_ss_2sm(tmem_d, da + (uint64_t)(2 * ks), db + (uint64_t)(2 * ks), idesc, (it | j | ks) != 0);
+                                else ptx::mma_f16_ss(tmem_d, da + (uint64_t)(2 * ks), db + (uint64_t)(2 * ks), idesc, (it | j | ks) != 0);
+                            }
                         }
                         if (CTAS == 2) ptx::mma_commit_2sm(empty_bar(stage), 3);    // frees the stage in both CTAs
                         else ptx::mma_commit(empty_bar(stage));
                     }
                     __syncwarp();
                     if (++stage == args.stages) { stage = 0; phase ^= 1u; }
-                    if (++kb == args.k_blocks) kb = 0;
+                    kb += args.kpack;
+                    if (kb >= args.k_blocks) kb = 0;
                 }
                 if (ptx::elect_one()) {
                     if (CTAS == 2) ptx::mma_commit_2sm(tfull_bar(acc_stage), 3);    // both CTAs' epilogues may start
@@ -579,7 +593,17 @@ int gemm_tcgen05_launch(const distb200_gemm_desc& d, cudaStream_t stream) {
     args.total_tiles = d.groups * args.tiles_per_group * args.n_tiles;
     DISTB200_REQUIRE(args.total_tiles < (1ll << 31) && d.groups < (1ll << 31), "gemm(tcgen05): too many tiles (%lld)", args.total_tiles);
     args.b_stage_bytes = (uint32_t)(args.block_n / args.ctas) * BLOCK_K * 2;
-    const uint32_t stage_bytes = A_STAGE_BYTES + args.b_stage_bytes;
+    // Several 64-wide k-blocks per pipeline stage when the MMA work of one k-block (proportional to block_n) is smaller than
+    // the barrier round trip of a stage: narrow tiles pack up to 4 k-blocks, wide ones up to 2; at least 3 stages must remain.
+    static const int kpack_env = getenv("DISTB200_GEMM_KPACK") ? atoi(getenv("DISTB200_GEMM_KPACK")) : 4;
+    args.kpack = 1;
+    {
+        const int limit = args.block_n <= 128 ? 4 : (args.block_n <= 192 ? 2 : 1);
+        // epilogue width is decided below from K; use the larger staging footprint for the budget check
+        for (int p = 2; p <= limit && p <= kpack_env; ++p)
+            if (args.k_blocks % p == 0 && 3 * p * (int)(A_STAGE_BYTES + args.b_stage_bytes) <= smem_budget(12)) args.kpack = p;
+    }
+    const uint32_t stage_bytes = (A_STAGE_BYTES + args.b_stage_bytes) * (uint32_t)args.kpack;
     // epilogue width: long reductions want the deepest operand ring, everything else the better latency hiding
     static const int ew_env = getenv("DISTB200_GEMM_EPI_WARPS") ? atoi(getenv("DISTB200_GEMM_EPI_WARPS")) : 0;
     const int ew = ew_env == 8 || ew_env == 12 ? ew_env : ((long long)d.k * d.num_taps >= 2048 ? 8 : 12);
