@@ -25,7 +25,7 @@ int check_launch(const char* what) {
     return 0;
 }
 
-int attention_simt_launch(const void* qkv, void* out, int frames, int tokens, int heads, int dtype, cudaStream_t stream);
+int attention_simt_launch(const void* qkv, void* out, int frames, int tokens, int heads, int dtype, bool causal, cudaStream_t stream);
 int attention_tc_launch(const void* qkv, void* out, int frames, int tokens, int heads, cudaStream_t stream);
 
 }  // namespace distb200
@@ -79,5 +79,13 @@ extern "C" int distb200_attention(const void* qkv, void* out, int32_t frames, in
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == DISTB200_BF16 && impl != DISTB200_IMPL_SIMT) return attention_tc_launch(qkv, out, frames, tokens, heads, st);
     DISTB200_REQUIRE(impl != DISTB200_IMPL_TCGEN05, "attention: the tensor-core kernel needs bf16");
-    return attention_simt_launch(qkv, out, frames, tokens, heads, dtype, st);
+    return attention_simt_launch(qkv, out, frames, tokens, heads, dtype, false, st);
+}
+
+extern "C" int distb200_attention_causal(const void* qkv, void* out, int32_t seqs, int32_t tokens, int32_t heads, int32_t dtype, void* stream) {
+    if (seqs == 0) return 0;
+    DISTB200_REQUIRE(qkv && out, "attention_causal: null pointer");
+    DISTB200_REQUIRE(tokens >= 1 && heads >= 1, "attention_causal: bad sizes");
+    DISTB200_REQUIRE(dtype == DISTB200_F32 || dtype == DISTB200_BF16, "attention_causal: unknown dtype %d", dtype);
+    return attention_simt_launch(qkv, out, seqs, tokens, heads, dtype, true, (cudaStream_t)stream);
 }

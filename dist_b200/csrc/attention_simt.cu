@@ -10,7 +10,9 @@ namespace {
 constexpr int HD = 64;
 constexpr int ATT_WARPS = 8;
 
-template <typename T>
+// CAUSAL: query i sees the keys j <= i only - the additive upper-triangular -inf mask of the CLIP text transformer
+// (clip.py:404-410); masked scores contribute exp(-inf) = 0 exactly, so they are simply not visited.
+template <typename T, bool CAUSAL>
 __global__ void __launch_bounds__(ATT_WARPS * 32) attention_simt_kernel(const T* __restrict__ qkv, T* __restrict__ out, int tokens, int heads) {
     grid_dep_sync();
     extern __shared__ float smem[];
@@ -34,8 +36,9 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) attention_simt_kernel(const T*
         qs[lane] = to_float(base[(long long)i * 3 * D + lane]) * 0.125f;
         qs[lane + 32] = to_float(base[(long long)i * 3 * D + lane + 32]) * 0.125f;
         __syncwarp();
+        const int keys = CAUSAL ? i + 1 : tokens;
         float mx = -INFINITY;
-        for (int j = lane; j < tokens; j += 32) {
+        for (int j = lane; j < keys; j += 32) {
             const float* kr = Ks + j * (HD + 1);
             float s = 0.f;
 #pragma unroll 16
@@ -45,7 +48,7 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) attention_simt_kernel(const T*
         }
         mx = warp_max(mx);
         float den = 0.f;
-        for (int j = lane; j < tokens; j += 32) {
+        for (int j = lane; j < keys; j += 32) {
             const float e = __expf(ps[j] - mx);
             ps[j] = e;
             den += e;
@@ -53,7 +56,7 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) attention_simt_kernel(const T*
         den = warp_sum(den);
         __syncwarp();
         float o0 = 0.f, o1 = 0.f;
-        for (int j = 0; j < tokens; ++j) {
+        for (int j = 0; j < keys; ++j) {
             const float pj = ps[j];
             o0 = fmaf(pj, Vs[j * HD + lane], o0);
             o1 = fmaf(pj, Vs[j * HD + lane + 32], o1);
@@ -68,18 +71,23 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) attention_simt_kernel(const T*
 
 }  // namespace
 
-int attention_simt_launch(const void* qkv, void* out, int frames, int tokens, int heads, int dtype, cudaStream_t stream) {
+template <typename T, bool CAUSAL>
+static void launch_variant(const void* qkv, void* out, unsigned grid, size_t smem, int tokens, int heads, cudaStream_t stream) {
+    static bool done = false;
+    if (!done) { cudaFuncSetAttribute(attention_simt_kernel<T, CAUSAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); done = true; }
+    DISTB200_LAUNCH((attention_simt_kernel<T, CAUSAL>), grid, ATT_WARPS * 32, smem, stream, (const T*)qkv, (T*)out, tokens, heads);
+}
+
+int attention_simt_launch(const void* qkv, void* out, int frames, int tokens, int heads, int dtype, bool causal, cudaStream_t stream) {
     const size_t smem = ((size_t)tokens * (HD + 1) + (size_t)tokens * HD + ATT_WARPS * HD + (size_t)ATT_WARPS * tokens) * sizeof(float);
     DISTB200_REQUIRE(smem <= 227 * 1024, "attention(simt): %d tokens need %zu bytes of shared memory", tokens, smem);
     const unsigned grid = (unsigned)frames * heads;
     if (dtype == DISTB200_F32) {
-        static bool done = false;
-        if (!done) { cudaFuncSetAttribute(attention_simt_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); done = true; }
-        DISTB200_LAUNCH(attention_simt_kernel<float>, grid, ATT_WARPS * 32, smem, stream, (const float*)qkv, (float*)out, tokens, heads);
+        if (causal) launch_variant<float, true>(qkv, out, grid, smem, tokens, heads, stream);
+        else launch_variant<float, false>(qkv, out, grid, smem, tokens, heads, stream);
     } else {
-        static bool done = false;
-        if (!done) { cudaFuncSetAttribute(attention_simt_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); done = true; }
-        DISTB200_LAUNCH(attention_simt_kernel<bf16>, grid, ATT_WARPS * 32, smem, stream, (const bf16*)qkv, (bf16*)out, tokens, heads);
+        if (causal) launch_variant<bf16, true>(qkv, out, grid, smem, tokens, heads, stream);
+        else launch_variant<bf16, false>(qkv, out, grid, smem, tokens, heads, stream);
     }
     return check_launch("attention_simt");
 }

@@ -20,7 +20,7 @@
 
 namespace distb200 {
 
-int attention_simt_launch(const void* qkv, void* out, int frames, int tokens, int heads, int dtype, cudaStream_t stream);
+int attention_simt_launch(const void* qkv, void* out, int frames, int tokens, int heads, int dtype, bool causal, cudaStream_t stream);
 
 namespace {
 
@@ -400,7 +400,7 @@ int attention_tc_launch(const void* qkv, void* out, int frames, int tokens, int 
     int keys_pad = (tokens + 15) / 16 * 16;
     const int keys_ld = keys_pad;
     if (keys_pad > 288 || ((uintptr_t)qkv & 15) || ((uintptr_t)out & 15))
-        return attention_simt_launch(qkv, out, frames, tokens, heads, DISTB200_BF16, stream);
+        return attention_simt_launch(qkv, out, frames, tokens, heads, DISTB200_BF16, false, stream);
 
     static EncodeTiledFn encode = nullptr;
     if (!encode) {

@@ -441,6 +441,47 @@ __global__ void __launch_bounds__(256) topk_correct_kernel(const float* __restri
             if (higher < ks[j]) atomicAdd(reinterpret_cast<unsigned long long*>(correct + j), 1ull);
 }
 
+// ---------------------------------------------------------------------------------------------------
+// CLIP text tower input / output rows (clip.py:419-434): token embedding lookup + positional embedding, and the row of
+// the end-of-text token (the largest id of a sequence; first occurrence, as torch.argmax returns it).
+__global__ void embed_tokens_kernel(const long long* __restrict__ ids, const float* __restrict__ table, const float* __restrict__ pos,
+                                    long long rows, int ctx, int width, float* __restrict__ out) {
+    grid_dep_sync();
+    const int w4 = width >> 2;
+    const long long total = rows * w4;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const long long r = idx / w4;
+        const int c = (int)(idx % w4);
+        const float4 e = reinterpret_cast<const float4*>(table + ids[r] * width)[c];
+        const float4 p = reinterpret_cast<const float4*>(pos + (r % ctx) * width)[c];
+        reinterpret_cast<float4*>(out + r * width)[c] = make_float4(e.x + p.x, e.y + p.y, e.z + p.z, e.w + p.w);
+    }
+}
+
+__global__ void gather_eot_kernel(const float* __restrict__ x, const long long* __restrict__ ids, int ctx, int width, float* __restrict__ out) {
+    grid_dep_sync();
+    __shared__ int s_best;
+    const long long s = blockIdx.x;
+    if (threadIdx.x < 32) {
+        long long best = ids[s * ctx];
+        int at = 0;
+        for (int i = threadIdx.x; i < ctx; i += 32) {
+            const long long v = ids[s * ctx + i];
+            if (v > best) { best = v; at = i; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const long long ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oa = __shfl_xor_sync(0xffffffffu, at, o);
+            if (ob > best || (ob == best && oa < at)) { best = ob; at = oa; }
+        }
+        if (threadIdx.x == 0) s_best = at;
+    }
+    __syncthreads();
+    const float* src = x + (s * ctx + s_best) * width;
+    for (int c = threadIdx.x; c < width; c += blockDim.x) out[s * width + c] = src[c];
+}
+
 inline unsigned grid_for(long long total, int block) {
     long long g = (total + block - 1) / block;
     const long long cap = (long long)sm_count() * 16;
@@ -617,4 +658,23 @@ extern "C" int distb200_class_head(const float* emb, const float* text_n, float 
     DISTB200_REQUIRE(smem <= 48 * 1024, "class_head: E + C too large for one block (%zu bytes)", smem);
     DISTB200_LAUNCH(class_head_kernel, batch, 256, smem, (cudaStream_t)stream, emb, text_n, scale, embed_dim, classes, logits, probs);
     return check_launch("class_head");
+}
+
+extern "C" int distb200_embed_tokens(const int64_t* ids, const float* table, const float* pos, int64_t seqs, int32_t ctx, int32_t width,
+                                     float* out, void* stream) {
+    if (seqs == 0) return 0;
+    DISTB200_REQUIRE(ids && table && pos && out, "embed_tokens: null pointer");
+    DISTB200_REQUIRE(ctx >= 1 && width >= 4 && width % 4 == 0, "embed_tokens: ctx=%d width=%d (width must be a multiple of 4)", ctx, width);
+    DISTB200_REQUIRE(((reinterpret_cast<uintptr_t>(table) | reinterpret_cast<uintptr_t>(pos) | reinterpret_cast<uintptr_t>(out)) & 15) == 0, "embed_tokens: alignment");
+    DISTB200_LAUNCH(embed_tokens_kernel, grid_for(seqs * ctx * (width / 4), 256), 256, 0, (cudaStream_t)stream, (const long long*)ids, table, pos,
+                    (long long)seqs * ctx, ctx, width, out);
+    return check_launch("embed_tokens");
+}
+
+extern "C" int distb200_gather_eot(const float* x, const int64_t* ids, int64_t seqs, int32_t ctx, int32_t width, float* out, void* stream) {
+    if (seqs == 0) return 0;
+    DISTB200_REQUIRE(x && ids && out, "gather_eot: null pointer");
+    DISTB200_REQUIRE(ctx >= 1 && width >= 1, "gather_eot: bad sizes");
+    DISTB200_LAUNCH(gather_eot_kernel, (unsigned)seqs, 128, 0, (cudaStream_t)stream, x, (const long long*)ids, ctx, width, out);
+    return check_launch("gather_eot");
 }

@@ -13,9 +13,9 @@ class ClipVisionTextTransformer(nn.Module):
 
     The reference permutes the clip to ``[B*T,3,H,W]`` before calling CLIP (``backbone.py:232-233``) and the DiST
     stem permutes it straight back (``dist.py:225``); both copies are dropped here - the CUDA path reads the
-    clip in its native ``[B,3,T,H,W]`` layout.  ``texts`` may be the int token matrix of the reference (only
-    usable when label embeddings were cached with ``set_text_features``; the text tower is outside this path)
-    or directly a float ``[C, E]`` label-embedding matrix.
+    clip in its native ``[B,3,T,H,W]`` layout.  ``texts`` is the int64 token matrix ``[C, ctx]`` of the reference
+    (encoded once by the CLIP text tower of the checkpoint, ``clip.py:436-452``; or ignored in favour of embeddings cached
+    with ``set_text_features``) or directly a float ``[C, E]`` label-embedding matrix.
     """
 
     def __init__(self, cfg):

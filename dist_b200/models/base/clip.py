@@ -4,8 +4,9 @@ The modules below own parameters under exactly the reference's ``state_dict`` na
 (SURVEY.md section 8b), so reference checkpoints load unchanged; their arithmetic runs in
 ``dist_b200.engine.DistEngine`` through the C ABI - torch layers such as ``nn.Linear`` or
 ``nn.MultiheadAttention`` appear here only as parameter containers and are never called.
-The text tower is outside this path: label embeddings enter as a constant ``[C, E]`` matrix
-(``set_text_features`` / ``others['label_embeddings']``, cf. ``clip.py:437-439``).
+Label embeddings enter either as token ids ``[C, ctx]`` - encoded ONCE by the CLIP text tower on the same CUDA library
+(``dist_b200/text.py``; ``cache_text``, ``clip.py:436-452``) when the checkpoint carries the tower - or as a constant
+``[C, E]`` matrix (``set_text_features`` / ``others['label_embeddings']``, ``clip.py:437-439``).
 """
 
 from collections import OrderedDict
@@ -43,6 +44,24 @@ class CrossAttentionBlockGenral(nn.Module):
         self.layer_id = layer_id
         self.attn = nn.MultiheadAttention(d_model, n_head)
         self.ln_1 = LayerNorm(d_model)
+
+
+class ResidualAttentionBlock(nn.Module):
+    """Block of the text transformer (``clip.py:112-136``, built with ``cfg=None`` at ``clip.py:205-208``): parameter holder,
+    evaluated by ``dist_b200.text.TextEngine`` with the causal mask of ``clip.py:404-410``."""
+
+    def __init__(self, d_model, n_head, attn_mask=None, cfg=None, layer_id=0):
+        super().__init__()
+        self.layer_id = layer_id
+        self.attn = nn.MultiheadAttention(d_model, n_head)
+        self.ln_1 = LayerNorm(d_model)
+        self.mlp = nn.Sequential(OrderedDict([
+            ("c_fc", nn.Linear(d_model, d_model * 4)),
+            ("gelu", QuickGELU()),
+            ("c_proj", nn.Linear(d_model * 4, d_model)),
+        ]))
+        self.ln_2 = LayerNorm(d_model)
+        self.is_image_transformer = attn_mask is None
 
 
 @ATTEN_BLOCK_REGISTRY.register()
@@ -112,10 +131,13 @@ class Transformer(nn.Module):
     def __init__(self, width, layers, heads, attn_mask=None, cfg=None):
         super().__init__()
         self.width, self.layers = width, layers
-        name = cfg.VIDEO.BACKBONE.ATTEN_BLOCK if cfg is not None else "ResidualAttentionBlockMid"
-        block = ATTEN_BLOCK_REGISTRY.get(name)
-        if block is None:
-            raise KeyError("attention block {!r} is not registered (the DiST configs select ResidualAttentionBlockMid)".format(name))
+        if cfg is None:                                                    # the text tower (clip.py:208-209)
+            block = ResidualAttentionBlock
+        else:
+            name = cfg.VIDEO.BACKBONE.ATTEN_BLOCK
+            block = ATTEN_BLOCK_REGISTRY.get(name)
+            if block is None:
+                raise KeyError("attention block {!r} is not registered (the DiST configs select ResidualAttentionBlockMid)".format(name))
         self.resblocks = nn.Sequential(*[block(width, heads, attn_mask, cfg=cfg, layer_id=i) for i in range(layers)])
 
 
@@ -177,7 +199,10 @@ class VisionTransformer(nn.Module):
 class CLIP(nn.Module):
     """``visual`` + ``dist_net`` + ``logit_scale``; forwards run the planned CUDA path."""
 
-    def __init__(self, cfg, embed_dim, image_resolution, vision_layers, vision_width, vision_patch_size, arch=None):
+    def __init__(self, cfg, embed_dim, image_resolution, vision_layers, vision_width, vision_patch_size, arch=None,
+                 context_length=None, vocab_size=None, transformer_width=None, transformer_heads=None, transformer_layers=None):
+        """The five text arguments are those of the reference (``clip.py:303-320``); ``None`` builds a model without the text
+        tower (label embeddings are then supplied as a matrix)."""
         super().__init__()
         from ..module_zoo.branches.dist import DiSTNetwork
         self.cfg = cfg
@@ -188,8 +213,17 @@ class CLIP(nn.Module):
         self.visual = VisionTransformer(cfg, image_resolution, vision_patch_size, vision_width, vision_layers,
                                         vision_width // 64, embed_dim)
         self.dist_net = DiSTNetwork(cfg, d_model=vision_width, width=vision_width, output_dim=embed_dim)
+        self.context_length, self.vocab_size = context_length, vocab_size
+        if transformer_width is not None:                                   # clip.py:360-370
+            self.transformer = Transformer(transformer_width, transformer_layers, transformer_heads, attn_mask="causal")
+            self.token_embedding = nn.Embedding(vocab_size, transformer_width)
+            self.positional_embedding = nn.Parameter(torch.empty(context_length, transformer_width).normal_(std=0.01))
+            self.ln_final = LayerNorm(transformer_width)
+            self.text_projection = nn.Parameter(torch.empty(transformer_width, embed_dim).normal_(std=transformer_width ** -0.5))
         self.logit_scale = nn.Parameter(torch.ones([]) * np.log(1 / 0.07))
         self.arch = arch
+        self._text_engine = None
+        self._text_cache = None
         b200 = getattr(cfg, "B200", None)
         self.precision = getattr(b200, "PRECISION", "bf16") if b200 is not None else "bf16"
         self.use_graph = bool(getattr(b200, "CUDA_GRAPH", True)) if b200 is not None else True
@@ -201,6 +235,37 @@ class CLIP(nn.Module):
         self.text_features = feats.detach().float()
         self._engines.clear()
 
+    @property
+    def has_text_tower(self):
+        return hasattr(self, "token_embedding")
+
+    def encode_text(self, text, others=None):
+        """``CLIP.encode_text`` (``clip.py:419-434``): ids int64 ``[C, ctx]`` -> ``(features [C, E], eot rows [C, W], others)``."""
+        from ...text import TextEngine
+        if not self.has_text_tower:
+            raise RuntimeError("this model was built without the CLIP text tower (its checkpoint has no transformer.* / "
+                               "token_embedding keys); supply label embeddings with set_text_features([C, E])")
+        dev = self.logit_scale.device
+        if dev.type != "cuda":
+            raise RuntimeError("dist_b200 runs on a CUDA device only; there is no CPU path (move the model with .cuda())")
+        names = ("transformer.", "token_embedding.", "positional_embedding", "ln_final.", "text_projection")
+        version = sum(p._version for n, p in self.named_parameters() if n.startswith(names))
+        key = (text.shape[0], str(dev), self.precision, version)
+        if self._text_engine is None or self._text_engine[0] != key:
+            sd = {k: v for k, v in self.state_dict().items() if k.startswith(names)}
+            self._text_engine = (key, TextEngine(sd, text.shape[0], device=dev, precision=self.precision))
+        feats, eot = self._text_engine[1].encode(text)
+        return feats.clone(), eot.clone(), others
+
+    def cache_text(self, text, others=None):
+        """``CLIP.cache_text`` (``clip.py:436-452``): the label set is encoded once and reused while its size is unchanged."""
+        if others is not None and "label_embeddings" in others:            # clip.py:437-439
+            return others["label_embeddings"], None, others
+        if self._text_cache is None or self._text_cache[0].shape[0] != text.shape[0]:
+            feats, eot, others = self.encode_text(text, others)
+            self._text_cache = (feats, eot)
+        return self._text_cache[0], self._text_cache[1], others
+
     def _text_from(self, text, others):
         if others is not None and "label_embeddings" in others:            # clip.py:437-439
             return others["label_embeddings"]
@@ -208,9 +273,13 @@ class CLIP(nn.Module):
             return text
         if self.text_features is not None:
             return self.text_features
+        if text is not None and self.has_text_tower:
+            if self.freeze_text:                                             # clip.py:483-486
+                return self.cache_text(text, others)[0]
+            return self.encode_text(text, others)[0]
         raise NotImplementedError(
-            "token ids were passed but no label embeddings are cached; the CLIP text tower is outside the DiST "
-            "forward path (SURVEY.md section 8f) - call set_text_features([C, E]) with embeddings computed once")
+            "token ids were passed, but this model has no CLIP text tower (its checkpoint carried none) and no label "
+            "embeddings are cached - call set_text_features([C, E]) with embeddings computed once")
 
     # ---- engine cache -------------------------------------------------------------------------
     def _engine(self, batch, device, text, input_format="float"):
@@ -280,8 +349,14 @@ class CLIP(nn.Module):
 
 def build_model(cfg, state_dict):
     """Infer the geometry from the checkpoint like ``clip.py:564-611`` and load it (``strict=False``)."""
+    from ...text import has_text_tower, text_geometry
     arch = arch_from_cfg(cfg, state_dict)
-    model = CLIP(cfg, arch.embed_dim, arch.resolution, arch.layers, arch.width, arch.patch, arch=arch)
+    tk = {}
+    if has_text_tower(state_dict):                                           # clip.py:586-591
+        g = text_geometry(state_dict)
+        tk = dict(context_length=g["context"], vocab_size=g["vocab"], transformer_width=g["width"], transformer_heads=g["heads"],
+                  transformer_layers=g["layers"])
+    model = CLIP(cfg, arch.embed_dim, arch.resolution, arch.layers, arch.width, arch.patch, arch=arch, **tk)
     own = model.state_dict()
     usable = {k: v for k, v in state_dict.items() if k in own and own[k].shape == v.shape}
     missing = sorted(set(own) - set(usable))

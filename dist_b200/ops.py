@@ -88,6 +88,9 @@ def lib():
     L.distb200_row_stats.argtypes = [vp, i32, i64, i64, i32, f32, vp, vp]
     L.distb200_attention.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp]
     L.distb200_cross_attention.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp]
+    L.distb200_attention_causal.argtypes = [vp, vp, i32, i32, i32, i32, vp]
+    L.distb200_embed_tokens.argtypes = [vp, vp, vp, i64, i32, i32, vp, vp]
+    L.distb200_gather_eot.argtypes = [vp, vp, i64, i32, i32, vp, vp]
     L.distb200_patchify.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i64, i32, vp]
     L.distb200_patchify_u8.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i64, i32, C.POINTER(C.c_float * 3), C.POINTER(C.c_float * 3), vp]
     L.distb200_view_ensemble.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, i64, vp]
@@ -111,7 +114,7 @@ def lib():
     for name in TRAIN_EXPORTS:
         getattr(L, name).restype = C.c_int
     for name in ("row_stats", "gemm", "layernorm", "attention", "cross_attention", "patchify", "patchify_u8", "rows_bcast", "mean_rows", "class_head", "view_ensemble",
-                 "topk_correct"):
+                 "topk_correct", "attention_causal", "embed_tokens", "gather_eot"):
         getattr(L, "distb200_" + name).restype = C.c_int
     assert L.distb200_version() == 100 and L.distb200_arch() == 100
     _LIB = L
@@ -124,7 +127,7 @@ TRAIN_EXPORTS = ("distb200_gemm_wgrad", "distb200_quickgelu", "distb200_quickgel
 
 EXPORTS = TRAIN_EXPORTS + ("distb200_version", "distb200_arch", "distb200_last_error", "distb200_gemm", "distb200_row_stats", "distb200_layernorm",
            "distb200_attention", "distb200_cross_attention", "distb200_patchify", "distb200_patchify_u8", "distb200_view_ensemble", "distb200_topk_correct", "distb200_rows_bcast",
-           "distb200_mean_rows", "distb200_class_head")
+           "distb200_mean_rows", "distb200_class_head", "distb200_attention_causal", "distb200_embed_tokens", "distb200_gather_eot")
 
 
 class DistB200Error(RuntimeError):
@@ -248,6 +251,32 @@ def attention(qkv, out, frames, tokens, heads, impl=IMPL_AUTO, name="attention")
     flops = 4 * frames * heads * tokens * tokens * 64
     nbytes = frames * tokens * heads * 64 * 4 * qkv.element_size()
     return Call(lib().distb200_attention, args, name, keep=(qkv, out), flops=flops, nbytes=nbytes)
+
+
+def attention_causal(qkv, out, seqs, tokens, heads, name="attention_causal"):
+    """Causal self attention of the CLIP text transformer (clip.py:404-410,122-124)."""
+    assert qkv.dtype == out.dtype
+    args = (qkv.data_ptr(), out.data_ptr(), int(seqs), int(tokens), int(heads), enum_of(qkv))
+    return Call(lib().distb200_attention_causal, args, name, keep=(qkv, out), flops=2 * seqs * heads * tokens * (tokens + 1) * 64,
+                nbytes=seqs * tokens * heads * 64 * 4 * qkv.element_size())
+
+
+def embed_tokens(ids, table, pos, out, name="embed_tokens"):
+    """out[s*ctx + i] = table[ids[s, i]] + pos[i]  (clip.py:420-421)"""
+    assert ids.dtype == torch.int64 and ids.is_contiguous() and table.dtype == pos.dtype == out.dtype == torch.float32
+    seqs, ctx = ids.shape
+    width = table.shape[1]
+    args = (ids.data_ptr(), table.data_ptr(), pos.data_ptr(), int(seqs), int(ctx), int(width), out.data_ptr())
+    return Call(lib().distb200_embed_tokens, args, name, keep=(ids, table, pos, out), nbytes=seqs * ctx * width * 12)
+
+
+def gather_eot(x, ids, out, name="gather_eot"):
+    """out[s] = x[s*ctx + argmax_i ids[s, i]]  (clip.py:429)"""
+    assert ids.dtype == torch.int64 and ids.is_contiguous() and x.dtype == out.dtype == torch.float32
+    seqs, ctx = ids.shape
+    width = out.shape[-1]
+    args = (x.data_ptr(), ids.data_ptr(), int(seqs), int(ctx), int(width), out.data_ptr())
+    return Call(lib().distb200_gather_eot, args, name, keep=(x, ids, out), nbytes=seqs * width * 8)
 
 
 def cross_attention(q, kv, out, batch, keys, heads, name="cross_attention"):

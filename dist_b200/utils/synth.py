@@ -202,6 +202,49 @@ def synth_text_features(num_classes, embed_dim, seed=77):
     return torch.randn(num_classes, embed_dim, generator=g, dtype=torch.float32)
 
 
+def synth_text_tower(embed_dim, width=512, layers=12, context=77, vocab=49408, seed=5, init="reference"):
+    """The CLIP text tower's tensors under the reference's key names (``clip.py:362-372``), drawn from the distributions of
+    ``CLIP.initialize_parameters`` (``clip.py:375-402``) for ``init="reference"``: token embedding N(0, 0.02), positional
+    embedding N(0, 0.01), attention / MLP weights N(0, width^-0.5 ...), ``text_projection`` N(0, width^-0.5)."""
+    assert width % 64 == 0 and init in ("reference", "scaled")
+    g = _Gen(seed, init)
+    sd = {}
+    ref = init == "reference"
+    sd["token_embedding.weight"] = (0.02 if ref else 0.5) * g.randn(vocab, width)
+    sd["positional_embedding"] = (0.01 if ref else 0.5) * g.randn(context, width)
+    proj_std = (width ** -0.5) * ((2 * layers) ** -0.5)
+    attn_std, fc_std = width ** -0.5, (2 * width) ** -0.5
+    for i in range(layers):
+        pre = "transformer.resblocks.%d" % i
+        sd[pre + ".attn.in_proj_weight"] = attn_std * g.randn(3 * width, width)
+        sd[pre + ".attn.in_proj_bias"] = g.bias(3 * width)
+        sd[pre + ".attn.out_proj.weight"] = (proj_std if ref else attn_std) * g.randn(width, width)
+        sd[pre + ".attn.out_proj.bias"] = g.bias(width)
+        _put_ln(sd, g, pre + ".ln_1", width)
+        sd[pre + ".mlp.c_fc.weight"] = (fc_std if ref else attn_std) * g.randn(4 * width, width)
+        sd[pre + ".mlp.c_fc.bias"] = g.bias(4 * width)
+        sd[pre + ".mlp.c_proj.weight"] = (proj_std if ref else (4 * width) ** -0.5) * g.randn(width, 4 * width)
+        sd[pre + ".mlp.c_proj.bias"] = g.bias(width)
+        _put_ln(sd, g, pre + ".ln_2", width)
+    _put_ln(sd, g, "ln_final", width)
+    sd["text_projection"] = (width ** -0.5) * g.randn(width, embed_dim)
+    return sd
+
+
+def synth_token_ids(num_prompts, context=77, vocab=49408, seed=11):
+    """Token ids shaped like the CLIP tokenizer's output (``dataset/utils/simple_tokenizer.py``): start-of-text = vocab-2,
+    1..context-2 word tokens, end-of-text = vocab-1 (the largest id, which ``encode_text`` locates by argmax), zero padding."""
+    g = torch.Generator(device="cpu")
+    g.manual_seed(int(seed))
+    ids = torch.zeros(num_prompts, context, dtype=torch.long)
+    for r in range(num_prompts):
+        n = int(torch.randint(1, context - 1, (1,), generator=g))
+        ids[r, 0] = vocab - 2
+        ids[r, 1:1 + n] = torch.randint(1, vocab - 2, (n,), generator=g)
+        ids[r, 1 + n] = vocab - 1
+    return ids
+
+
 def synth_soft_targets(batch, num_classes, seed=99, smoothing=0.1):
     """Soft labels ``[b, C]`` of the kind mixup / cutmix + label smoothing produce (``dataset/utils/mixup.py:103-319``):
     each row mixes two smoothed one-hot labels with a Beta(0.8, 0.8)-like weight and sums to one."""

@@ -129,6 +129,21 @@ int distb200_row_stats(const void* x, int32_t dtype, int64_t ld, int64_t rows, i
 int distb200_attention(const void* qkv, void* out, int32_t frames, int32_t tokens, int32_t heads,
                        int32_t dtype, int32_t impl, void* stream);
 
+/* Causal multi-head self attention of the CLIP text transformer: token i attends to the tokens j <= i (the additive
+ * upper-triangular -inf mask built at clip.py:404-410 and passed to nn.MultiheadAttention at clip.py:122-124).  Same layout as
+ * distb200_attention.  FFMA kernel for both dtypes: the label set is encoded once and cached (clip.py:436-452). */
+int distb200_attention_causal(const void* qkv, void* out, int32_t seqs, int32_t tokens, int32_t heads, int32_t dtype,
+                              void* stream);
+
+/* Text tower input rows (clip.py:420-421): out[s*ctx + i, :] = table[ids[s*ctx + i], :] + pos[i, :], fp32.  ids int64 on the
+ * device, every id in [0, vocab) (checked by the caller: nn.Embedding raises on the host). */
+int distb200_embed_tokens(const int64_t* ids, const float* table, const float* pos, int64_t seqs, int32_t ctx, int32_t width,
+                          float* out, void* stream);
+
+/* Text tower output rows (clip.py:429): out[s, :] = x[s*ctx + argmax_i ids[s, i], :] - the end-of-text token has the largest
+ * id of its sequence; ties resolve to the first position like torch.argmax. */
+int distb200_gather_eot(const float* x, const int64_t* ids, int64_t seqs, int32_t ctx, int32_t width, float* out, void* stream);
+
 /* Single-query cross attention (CrossAttentionBlockGenral inside the ada-pooling head, clip.py:139-147,
  * dist.py:144,158): q [batch, heads*64]; kv [batch, keys, 2*heads*64] (k | v); out [batch, heads*64]. */
 int distb200_cross_attention(const void* q, const void* kv, void* out, int32_t batch, int32_t keys,

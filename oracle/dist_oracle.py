@@ -263,6 +263,31 @@ def class_scores(sd, emb, text_features, softmax=True):
     return torch.softmax(logits, dim=-1) if softmax else logits
 
 
+def encode_text(sd, ids):
+    """CLIP text tower (``CLIP.encode_text``, clip.py:419-434; blocks = ``ResidualAttentionBlock``, clip.py:112-136, with the
+    causal additive mask of clip.py:404-410).  ids int64 [C, ctx] -> (features [C, E], eot rows [C, W])."""
+    W = sd["ln_final.weight"].shape[0]
+    heads = W // 64                                                                 # clip.py:590
+    layers = len({k.split(".")[2] for k in sd if k.startswith("transformer.resblocks.")})
+    x = sd["token_embedding.weight"][ids] + sd["positional_embedding"]              # [C, ctx, W]
+    C, ctx, _ = x.shape
+    mask = torch.full((ctx, ctx), float("-inf"), dtype=x.dtype).triu_(1)
+    for l in range(layers):
+        pre = "transformer.resblocks.%d." % l
+        y = _ln(x, sd[pre + "ln_1.weight"], sd[pre + "ln_1.bias"])
+        w, bias = sd[pre + "attn.in_proj_weight"], sd[pre + "attn.in_proj_bias"]
+        q, k, v = (y @ w.t() + bias).split(W, dim=-1)
+        sp = lambda z: z.view(C, ctx, heads, 64).transpose(1, 2)
+        att = torch.softmax(sp(q) @ sp(k).transpose(-1, -2) / 8.0 + mask, dim=-1)
+        o = (att @ sp(v)).transpose(1, 2).reshape(C, ctx, W)
+        x = x + _lin(o, sd, pre + "attn.out_proj")
+        y = _ln(x, sd[pre + "ln_2.weight"], sd[pre + "ln_2.bias"])
+        x = x + _lin(_qgelu(_lin(y, sd, pre + "mlp.c_fc")), sd, pre + "mlp.c_proj")
+    eot = x[torch.arange(C), ids.argmax(dim=-1)]                                     # clip.py:429
+    feats = _ln(eot, sd["ln_final.weight"], sd["ln_final.bias"]) @ sd["text_projection"]
+    return feats, eot
+
+
 def forward(sd, video, alpha, selected_layers, s_patch, ada_layers, dtype=torch.float64, return_parts=False):
     """Whole path: [b, 3, T, H, W] -> [b, E] (= CLIP.forward_without_text(...)[:, 0], clip.py:466-480)."""
     sd = {k: v.to(dtype) for k, v in sd.items() if k.startswith(("visual.", "dist_net.", "logit_scale"))}

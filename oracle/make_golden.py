@@ -105,11 +105,18 @@ def _text_tower_stub(arch, width=64, layers=1, ctx=8, vocab=32):
     return sd
 
 
-def build_reference(arch, sd):
+TEXT_CASES = {
+    # name: (visual arch, text tower kwargs, weight init, prompts, clips)
+    "text_tiny": (tiny_arch(), dict(width=128, layers=2, context=12, vocab=64), "scaled", 10, 2),
+    "text_b16": (tiny_arch(embed_dim=512, num_classes=16), dict(width=512, layers=12, context=77, vocab=49408), "reference", 16, 1),
+}
+
+
+def build_reference(arch, sd, text_sd=None):
     from models.base import clip
     cfg = _reference_cfg(arch)
     full = dict(sd)
-    full.update(_text_tower_stub(arch))
+    full.update(text_sd if text_sd is not None else _text_tower_stub(arch))
     model = clip.build_model(cfg, dict(full))
     want = {k for k in model.state_dict() if k.startswith(("visual.", "dist_net."))}
     have = {k for k in sd if k.startswith(("visual.", "dist_net."))}
@@ -118,8 +125,46 @@ def build_reference(arch, sd):
     for k in have:
         assert msd[k].shape == sd[k].shape, (k, msd[k].shape, sd[k].shape)
         assert torch.equal(msd[k], sd[k]), k
+    if text_sd is not None:
+        for k, v in text_sd.items():
+            assert msd[k].shape == v.shape and torch.equal(msd[k], v), k
     model.prediction_fusion_enable = False          # undefined attribute read at clip.py:519
     return model.eval()
+
+
+def run_text_case(name):
+    """Text tower: ``CLIP.encode_text`` (clip.py:419-434) and the token-id entry of ``CLIP.forward``
+    (clip.py:482-533 with FREEZE_TEXT -> cache_text) on seeded synthetic weights and tokenizer-shaped ids."""
+    arch, tk, init, prompts, batch = TEXT_CASES[name]
+    t0 = time.time()
+    sd = synth.synth_state_dict(arch, seed=0, init=init if init == "scaled" else "reference")
+    tsd = synth.synth_text_tower(arch.embed_dim, seed=5, init=init, **tk)
+    ids = synth.synth_token_ids(prompts, tk["context"], tk["vocab"], seed=11)
+    clips = synth.synth_clips(batch, arch, seed=1234, kind="structured")
+    model = build_reference(arch, sd, tsd)
+    frames = clips.permute(0, 2, 1, 3, 4).reshape(batch * arch.frames, 3, arch.resolution, arch.resolution)
+    with torch.no_grad():
+        feats, eot, _ = model.encode_text(ids, None)                                  # clip.py:419
+        out = model(frames, ids)                                                      # clip.py:460 -> cache_text -> encode_text
+    logits = out["logits_per_image"]
+    tsd64 = {k: v.double() for k, v in tsd.items()}
+    o_feats, o_eot = dist_oracle.encode_text(tsd64, ids)
+    o_emb = dist_oracle.forward_arch(sd, clips, arch, dtype=torch.float64)
+    o_logits = dist_oracle.class_scores({k: v.double() for k, v in sd.items()}, o_emb, o_feats, softmax=False)
+    rel = lambda a, ref: float((a.double() - ref.double()).norm() / ref.double().norm())
+    errs = {"feats": rel(o_feats, feats), "eot": rel(o_eot, eot), "logits": rel(o_logits, logits)}
+    print("[%s] reference+oracle %.1fs; oracle-vs-reference rel-L2: %s" % (name, time.time() - t0, {k: "%.2e" % v for k, v in errs.items()}))
+    assert max(errs.values()) < 2e-6, errs
+    fixture = {
+        "case": name, "init": init, "arch": dict(arch.__dict__), "text": dict(tk), "prompts": prompts, "batch": batch,
+        "weight_seed": 0, "text_seed": 5, "ids_seed": 11, "clip_seed": 1234,
+        "text_checksum": synth.checksum(tsd), "ids": ids.clone(),
+        "feats": feats.float().clone(), "eot": eot.float().clone(), "logits": logits.float().clone(),
+        "oracle_vs_reference": errs, "torch": torch.__version__,
+    }
+    path = os.path.join(REPO, "tests", "golden", name + ".pt")
+    torch.save(fixture, path)
+    print("    wrote %s (%.1f KB)" % (path, os.path.getsize(path) / 1024))
 
 
 def _sub(x, step_rows, step_cols):
@@ -218,9 +263,9 @@ def main():
     sys.path.insert(0, REF)
     os.chdir(REF)                      # base.yaml is cwd-relative (utils/config.py:86)
     import models.base                 # noqa: F401  (registration side effects, models/base/__init__.py)
-    names = sys.argv[1:] or list(CASES)
+    names = sys.argv[1:] or (list(CASES) + list(TEXT_CASES))
     for n in names:
-        run_case(n)
+        (run_text_case if n in TEXT_CASES else run_case)(n)
 
 
 if __name__ == "__main__":
