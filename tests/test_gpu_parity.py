@@ -270,3 +270,23 @@ def test_stand_alone_attention_block_protocol():
     h = h + dist_oracle._lin(dist_oracle._qgelu(dist_oracle._lin(t, sd64, pre + "mlp.c_fc")), sd64, pre + "mlp.c_proj")
     assert y.shape == x.shape and rel_l2(y.permute(1, 0, 2), h) < 1e-2
     assert torch.equal(others["mid_feat"]["img"][1], y)
+
+
+def test_two_branch_graph_is_race_free_b16():
+    """Optionally the captured graph runs the ViT and the DiST chains as parallel branches (engine.plan_branches).  At the full B/16
+    geometry every kernel fills the GPU, so a missing edge would show as a changed embedding: replays must be bit-identical
+    to the single-stream eager run, with fresh clips each time (the tap buffers are reused across replays)."""
+    from dist_b200.arch import DistArch
+    from dist_b200.engine import DistEngine
+    from dist_b200.utils import synth
+    arch = DistArch().validate()
+    sd = synth.synth_state_dict(arch, seed=0, init="scaled")
+    eng = DistEngine(sd, arch, 8, device="cuda", precision="bf16", text_features=synth.synth_text_features(arch.num_classes, arch.embed_dim))
+    batches = [synth.synth_clips(8, arch, seed=s, kind="structured").cuda() for s in (1, 2, 3)]
+    eager = [eng.forward(v, use_graph=False).clone() for v in batches]
+    eng.capture(branches=2)
+    assert eng.graph_branches == 2
+    for rep in range(3):
+        for v, want in zip(batches, eager):
+            got = eng.forward(v, use_graph=True).clone()
+            assert torch.equal(got, want), "replay %d differs from the eager run" % rep

@@ -184,3 +184,30 @@ def test_checkpoint_ingest_roundtrip_and_legacy_names(tmp_path):
     torch.save({"model_state": legacy}, path)
     back = checkpoint.load_state_dict(path)
     assert sorted(back) == sorted(sd) and all(torch.equal(back[k], sd[k]) for k in sd)
+
+
+def test_graph_branches_dependencies():
+    """The two-branch CUDA graph (engine.plan_branches): ViT calls on branch 0, DiST calls on branch 1, and exactly the
+    cross-branch edges the tap buffers require (taps alternate between two buffers by ViT block)."""
+    from dist_b200.engine import plan_branches
+    sel = [0, 2, 3]
+    names = ["patchify.dense", "vit.patch_embed", "vit.cls_rows", "vit.ln_pre", "dist.stem"]
+    for l in range(4):
+        names += ["vit.ln_1" if l == 0 else "vit.ln_1.stats", "vit.qkv", "vit.attention", "vit.out_proj", "vit.ln_2.stats", "vit.fc1", "vit.fc2"]
+        if l in sel:
+            names += ["dist.tn.ln", "dist.tn.conv_s", "dist.input_linear", "dist.t2i", "dist.int.proj"]
+        if l == sel[-1]:
+            names.append("dist.cls_mean")
+    names += ["ada.init_sp", "tail.proj_spatial_cls", "tail.proj", "head.class_scores"]
+    branch, deps = plan_branches(names, sel)
+    at = lambda n, j: [k for k, x in enumerate(names) if x == n][j]
+    assert all(branch[k] == (0 if n.startswith(("patchify", "vit.")) or n == "dist.cls_mean" else 1) for k, n in enumerate(names))
+    assert deps[at("dist.stem", 0)] == [at("patchify.dense", 0)]
+    for i, l in enumerate(sel):                                   # DiST layer i reads the tap of block sel[i]
+        assert deps[at("dist.input_linear", i)] == [at("vit.fc2", l)]
+    assert deps[at("vit.fc2", 2)] == [at("dist.input_linear", 0)]  # block 2 overwrites the buffer of block 0, read by DiST layer 0
+    assert at("vit.fc2", 3) not in deps                            # block 1 is not tapped: nothing to wait for
+    assert at("vit.fc2", 0) not in deps and at("vit.fc2", 1) not in deps
+    assert deps[at("tail.proj_spatial_cls", 0)] == [at("dist.cls_mean", 0)]
+    for k, ds in deps.items():                                    # every edge points backwards in plan order and crosses branches
+        assert all(d < k and branch[d] != branch[k] for d in ds)
