@@ -49,6 +49,7 @@ extern "C" int distb200_gemm(const distb200_gemm_desc* desc, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (d.impl == DISTB200_IMPL_SIMT || d.dtype == DISTB200_F32) {
         DISTB200_REQUIRE(d.impl == DISTB200_IMPL_AUTO || d.impl == DISTB200_IMPL_SIMT, "gemm: the tcgen05 kernels need bf16 operands");
+        DISTB200_REQUIRE(!d.stat_partials, "gemm: stat_partials is emitted by the tcgen05 epilogue only");
         return gemm_simt_launch(d, st);
     }
     return gemm_tcgen05_launch(d, st);

@@ -114,7 +114,8 @@ __device__ __forceinline__ void stage_block(const uint32_t* acc, float* stage, i
 //   OUT:  0 = fp32 `out`, 1 = bf16 `out`, 2 = fp32 `out` + bf16 `out2`, 3 = anything (runtime flags)
 //   ACT:  0 none, 1 QuickGELU via tanh.approx.f16x2, 2 QuickGELU via ex2 + rcp
 // LNF: LayerNorm folded into the GEMM (see distb200_gemm_desc.ln_stats): acc -> rstd * (acc - mean * wsum[n]) + bias[n]
-template <int OUT, bool RES, int ACT, bool LNF = false>
+// STATS: per-row sum / sum of squares of the bf16 values written to out2 (distb200_gemm_desc.stat_partials), accumulated in st[]
+template <int OUT, bool RES, int ACT, bool LNF = false, bool STATS = false>
 struct Epi {
     // Column domain: eight lanes cover the 32 columns of a row (four adjacent columns = 16 bytes each), the four
     // lane groups take four consecutive rows.  One loop iteration = four rows: 512 B of fp32 (256 B of bf16) per warp
@@ -145,7 +146,7 @@ struct Epi {
 
     template <bool FULL>
     static __device__ __forceinline__ void finish_rows(const distb200_gemm_desc& d, const float* stage, const float4* rv, const float4 bias,
-                                                       const float4 ws, int lane, int n, int rows_here, long long dst_row0) {
+                                                       const float4 ws, int lane, int n, int rows_here, long long dst_row0, float2* st) {
         const int sub = lane >> 3, chunk = lane & 7;
         char* o1 = nullptr;
         char* o2 = nullptr;
@@ -196,7 +197,16 @@ struct Epi {
                 }
                 if (o2) {
                     if (f32_2) *reinterpret_cast<float4*>(o2) = v;
-                    else *reinterpret_cast<uint2*>(o2) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+                    else {
+                        const uint32_t p0 = pack_bf16x2(v.x, v.y), p1 = pack_bf16x2(v.z, v.w);
+                        *reinterpret_cast<uint2*>(o2) = make_uint2(p0, p1);
+                        if (STATS) {            // statistics of exactly the values the consuming GEMM will read
+                            const float a = __uint_as_float(p0 << 16), b = __uint_as_float(p0 & 0xffff0000u);
+                            const float c = __uint_as_float(p1 << 16), e = __uint_as_float(p1 & 0xffff0000u);
+                            st[i].x += (a + b) + (c + e);
+                            st[i].y += fmaf(a, a, b * b) + fmaf(c, c, e * e);
+                        }
+                    }
                 }
             }
             o1 += s1;
@@ -205,9 +215,9 @@ struct Epi {
     }
 
     static __device__ __forceinline__ void finish(const distb200_gemm_desc& d, const float* stage, const float4* rv, const float4 bias,
-                                                  const float4 ws, int lane, int n, int rows_here, long long dst_row0) {
-        if (rows_here >= 32) finish_rows<true>(d, stage, rv, bias, ws, lane, n, rows_here, dst_row0);
-        else finish_rows<false>(d, stage, rv, bias, ws, lane, n, rows_here, dst_row0);
+                                                  const float4 ws, int lane, int n, int rows_here, long long dst_row0, float2* st) {
+        if (rows_here >= 32) finish_rows<true>(d, stage, rv, bias, ws, lane, n, rows_here, dst_row0, st);
+        else finish_rows<false>(d, stage, rv, bias, ws, lane, n, rows_here, dst_row0, st);
     }
 };
 
@@ -237,11 +247,16 @@ __device__ __forceinline__ EpiTile epi_tile(const TcArgs& args, long long tile, 
 // chunk i+1 is requested before chunk i is processed, so that a warp always has one chunk of loads (4 KB) in
 // flight while it transposes, activates and stores another: the epilogue of the narrow, short-K GEMMs is bound by
 // the latency of these loads, not by their bandwidth.
-template <int OUT, bool RES, int ACT, int EW, bool LNF = false>
+template <int OUT, bool RES, int ACT, int EW, bool LNF = false, bool STATS = false>
 __device__ __forceinline__ void epilogue_role(const TcArgs& args, uint32_t tmem_base, float* stage, uint32_t tfull0, uint32_t tempty0,
                                               int warp, int lane, long long tile0, long long tile_step, int rank) {
-    typedef Epi<OUT, RES, ACT, LNF> E;
+    typedef Epi<OUT, RES, ACT, LNF, STATS> E;
     const distb200_gemm_desc& d = args.d;
+    float2 st[STATS ? 8 : 1];                // rows 4*i + sub of this warp's quadrant: (sum, sum of squares) over the warp's chunks of the tile
+    if (STATS) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) st[i] = make_float2(0.f, 0.f);
+    }
     const int quad = warp & 3;              // TMEM lanes [32*quad, 32*quad+32) are the ones this warp may read
     const int half = (warp - 2) >> 2;       // which of the alternating 32-column chunks
     const int sub = lane >> 3, cl = (lane & 7) * 4;
@@ -293,7 +308,7 @@ __device__ __forceinline__ void epilogue_role(const TcArgs& args, uint32_t tmem_
                 __syncwarp();
                 for (int rep = 0; rep < d.out_rep; ++rep) {
                     if (rep > 0) E::prefetch(d, rv, bias, ws, cur.res0 + (long long)rep * d.res_rep_stride, cur.srow0, n, sub, cur.rows_valid, col_ok);
-                    if (col_ok) E::finish(d, stage, rv, bias, ws, lane, n, cur.rows_valid, cur.dst0 + (long long)rep * d.out_rep_stride);
+                    if (col_ok) E::finish(d, stage, rv, bias, ws, lane, n, cur.rows_valid, cur.dst0 + (long long)rep * d.out_rep_stride, st);
                 }
                 __syncwarp();
             }
@@ -308,6 +323,22 @@ __device__ __forceinline__ void epilogue_role(const TcArgs& args, uint32_t tmem_
             }
             if (++acc_stage == 2) { acc_stage = 0; acc_phase ^= 1u; }
             waited = false;
+            if (STATS) {
+                // The tile is done: fold the eight lanes of every row together and publish this warp's slot of the row statistics.
+                const int slot = (cur.n0 / args.block_n) * (EW / 4) + half;
+                float2* dst = reinterpret_cast<float2*>(d.stat_partials) + (cur.srow0 + sub) * DISTB200_STAT_SLOTS + slot;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    float a = st[i].x, q = st[i].y;
+#pragma unroll
+                    for (int o = 1; o < 8; o <<= 1) {
+                        a += __shfl_xor_sync(0xffffffffu, a, o);
+                        q += __shfl_xor_sync(0xffffffffu, q, o);
+                    }
+                    if ((lane & 7) == 0 && 4 * i + sub < cur.rows_valid) dst[4 * i * DISTB200_STAT_SLOTS] = make_float2(a, q);
+                    st[i] = make_float2(0.f, 0.f);
+                }
+            }
             if (next_tile >= args.total_tiles) break;
         }
         tile = next_tile;
@@ -504,6 +535,7 @@ __global__ void __launch_bounds__(num_threads(EW), 1) gemm_tcgen05_kernel(const 
         } else if (bf_only && !d.res && !gelu) DISTB200_EPI(1, false, 0);
         else if (bf_only && !d.res && gelu) DISTB200_EPI(1, false, 1);
         else if (f_only && d.res && !gelu) DISTB200_EPI(0, true, 0);
+        else if (f_and_bf && d.res && !gelu && d.stat_partials) epilogue_role<2, true, 0, EW, false, true>(args, tmem_base, stage, tf, te, warp, lane, tile0, tile_step, rank);
         else if (f_and_bf && d.res && !gelu) DISTB200_EPI(2, true, 0);
         else if (f_and_bf && d.res && gelu) DISTB200_EPI(2, true, 2);
         else if (d.res) {
@@ -558,6 +590,12 @@ int gemm_tcgen05_launch(const distb200_gemm_desc& d, cudaStream_t stream) {
                         "gemm(tcgen05): ln_stats / ln_wsum alignment");
     }
 
+    if (d.stat_partials) {
+        DISTB200_REQUIRE(d.out && d.out_dtype == DISTB200_F32 && d.out2 && d.out2_dtype == DISTB200_BF16 && d.res && d.act == DISTB200_ACT_NONE &&
+                        d.out_rep == 1 && !d.ln_stats, "gemm(tcgen05): stat_partials needs fp32 out + bf16 out2 + res, no activation, out_rep 1");
+        DISTB200_REQUIRE((reinterpret_cast<uintptr_t>(d.stat_partials) & 7) == 0, "gemm(tcgen05): stat_partials alignment");
+    }
+
     TcArgs args;
     args.d = d;
     args.group_dim = d.group_dim == 3 ? 3 : 2;
@@ -607,6 +645,8 @@ int gemm_tcgen05_launch(const distb200_gemm_desc& d, cudaStream_t stream) {
     // epilogue width: long reductions want the deepest operand ring, everything else the better latency hiding
     static const int ew_env = getenv("DISTB200_GEMM_EPI_WARPS") ? atoi(getenv("DISTB200_GEMM_EPI_WARPS")) : 0;
     const int ew = ew_env == 8 || ew_env == 12 ? ew_env : ((long long)d.k * d.num_taps >= 2048 ? 8 : 12);
+    DISTB200_REQUIRE(!d.stat_partials || args.n_tiles * (ew / 4) <= DISTB200_STAT_SLOTS,
+                    "gemm(tcgen05): %d column tiles x %d epilogue phases exceed the %d statistic slots", args.n_tiles, ew / 4, DISTB200_STAT_SLOTS);
     args.stages = smem_budget(ew) / (int)stage_bytes;
     if (args.stages > MAX_STAGES) args.stages = MAX_STAGES;
     if (args.stages < 2) args.stages = 2;

@@ -580,6 +580,30 @@ __global__ void gather_eot_kernel(const float* __restrict__ x, const long long* 
     for (int c = threadIdx.x; c < width; c += blockDim.x) out[s * width + c] = src[c];
 }
 
+// (mean, rstd) from the statistic slots a GEMM epilogue emitted (distb200_gemm_desc.stat_partials): 8 lanes per row, two slots each
+__global__ void __launch_bounds__(256) row_stats_finalize_kernel(const float4* __restrict__ partials, long long rows, float inv_cols, float eps,
+                                                                 float2* __restrict__ stats) {
+    grid_dep_sync();
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long row = idx >> 3;
+    const int part = (int)(idx & 7);
+    float s = 0.f, q = 0.f;
+    if (row < rows) {
+        const float4 v = __ldcs(partials + row * (DISTB200_STAT_SLOTS / 2) + part);      // slots 2*part, 2*part + 1
+        s = v.x + v.z;
+        q = v.y + v.w;
+    }
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        q += __shfl_xor_sync(0xffffffffu, q, o);
+    }
+    if (row < rows && part == 0) {
+        const float mean = s * inv_cols;
+        stats[row] = make_float2(mean, rsqrtf(fmaxf(q * inv_cols - mean * mean, 0.f) + eps));
+    }
+}
+
 // persistent LayerNorm grid: every resident block slot of the device, fewer when the rows do not fill them
 inline unsigned ln_grid(long long rows, int rows_per_block, int blocks_per_sm) {
     const long long want = (rows + rows_per_block - 1) / rows_per_block, cap = (long long)sm_count() * blocks_per_sm;
@@ -791,4 +815,14 @@ extern "C" int distb200_gather_eot(const float* x, const int64_t* ids, int64_t s
     DISTB200_REQUIRE(ctx >= 1 && width >= 1, "gather_eot: bad sizes");
     DISTB200_LAUNCH(gather_eot_kernel, (unsigned)seqs, 128, 0, (cudaStream_t)stream, x, (const long long*)ids, ctx, width, out);
     return check_launch("gather_eot");
+}
+
+extern "C" int distb200_row_stats_finalize(const float* stat_partials, int64_t rows, int32_t cols, float eps, float* stats, void* stream) {
+    if (rows == 0) return 0;
+    DISTB200_REQUIRE(stat_partials && stats && cols >= 1, "row_stats_finalize: bad arguments");
+    DISTB200_REQUIRE((reinterpret_cast<uintptr_t>(stat_partials) & 15) == 0 && (reinterpret_cast<uintptr_t>(stats) & 7) == 0, "row_stats_finalize: alignment");
+    static_assert(DISTB200_STAT_SLOTS == 16, "the finalize kernel reads eight float4 per row");
+    DISTB200_LAUNCH(row_stats_finalize_kernel, (unsigned)((rows * 8 + 255) / 256), 256, 0, (cudaStream_t)stream, reinterpret_cast<const float4*>(stat_partials),
+                    (long long)rows, 1.0f / (float)cols, eps, reinterpret_cast<float2*>(stats));
+    return check_launch("row_stats_finalize");
 }

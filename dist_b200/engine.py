@@ -234,9 +234,19 @@ class DistEngine:
         self.tap = self.taps[0]
         # LayerNorm folded into the QKV / FC1 GEMMs (bf16 path): bf16 copies of the residual stream + per-row statistics
         self.ln_fold = self.precision == "bf16" and os.environ.get("DISTB200_LN_FOLD", "1") != "0"
+        # ... and the statistics themselves come out of the producing GEMM's epilogue (distb200_gemm_desc.stat_partials) instead of a
+        # separate pass over the bf16 copy: one slot buffer per producer shape (FC2 -> ln_1, out_proj -> ln_2)
+        # Measured (B/16 8+16f, 32 clips, per step): FC2 is tensor-bound and its epilogue has slack - emitting the statistics costs it
+        # +0.03 ms and removes 0.18 ms of row_stats; out_proj is bound by its epilogue / the fp32 stream and loses +0.18 ms for the
+        # 0.19 ms it saves.  Hence mode 2 by default (0: stand-alone row_stats, 1: both producers, 2: FC2 only).
+        mode = os.environ.get("DISTB200_LN_STATS_FUSED", "2")
+        self.stats_fused = self.ln_fold and mode != "0"
+        self.stats_fused_out_proj = self.stats_fused and mode != "2"
         if self.ln_fold:
             self.hb_mid = z(Mv, D)
             self.row_st = z(Mv, 2, dtype=f32)
+            if self.stats_fused:
+                self.stat_p = [z(Mv, ops.STAT_SLOTS, 2, dtype=f32), z(Mv, ops.STAT_SLOTS, 2, dtype=f32)]
         self._hb_prev = None
         self.xT = z(Mt, Ct, dtype=f32)
         self.xT_a = z(Mt, Ct)
@@ -369,20 +379,29 @@ class DistEngine:
         F, N = self.batch * a.sparse_frames, a.tokens
         add = self.calls.append
         fold = self.ln_fold
+        fused = fold and getattr(self, "stats_fused", False)
+        D = a.width
         if fold and self._hb_prev is not None:
-            add(ops.row_stats(self._hb_prev, self.row_st, name="vit.ln_1.stats"))
+            if fused:
+                add(ops.row_stats_finalize(self.stat_p[0], D, self.row_st, name="vit.ln_1.stats"))
+            else:
+                add(ops.row_stats(self._hb_prev, self.row_st, name="vit.ln_1.stats"))
             self._lin(self._hb_prev, v["qkv_wf"], v["qkv_bf"], self.qkv, ln_stats=self.row_st, ln_wsum=v["qkv_ws"], name="vit.qkv")
         else:
             self._ln(self.h, v["ln1"], self.ln_buf, name="vit.ln_1")
             self._lin(self.ln_buf, v["qkv_w"], v["qkv_b"], self.qkv, name="vit.qkv")
         add(ops.attention(self.qkv, self.attn_out, F, N, a.heads, impl=self.attn_impl, name="vit.attention"))
         if fold:
-            self._lin(self.attn_out, v["proj_w"], v["proj_b"], self.h, res=self.h, out2=self.hb_mid, name="vit.out_proj")
-            add(ops.row_stats(self.hb_mid, self.row_st, name="vit.ln_2.stats"))
+            self._lin(self.attn_out, v["proj_w"], v["proj_b"], self.h, res=self.h, out2=self.hb_mid, name="vit.out_proj",
+                      stat_partials=self.stat_p[1] if (fused and self.stats_fused_out_proj) else None)
+            if fused and self.stats_fused_out_proj:
+                add(ops.row_stats_finalize(self.stat_p[1], D, self.row_st, name="vit.ln_2.stats"))
+            else:
+                add(ops.row_stats(self.hb_mid, self.row_st, name="vit.ln_2.stats"))
             self._lin(self.hb_mid, v["fc1_wf"], v["fc1_bf"], self.fc1, act=ops.ACT_QUICKGELU, ln_stats=self.row_st, ln_wsum=v["fc1_ws"],
                       name="vit.fc1")
             hb = tap_out if tap_out is not None else self.taps[l % 2]   # bf16 copy of the block output: the tap AND the next block's operand
-            self._lin(self.fc1, v["fc2_w"], v["fc2_b"], self.h, res=self.h, out2=hb, name="vit.fc2")
+            self._lin(self.fc1, v["fc2_w"], v["fc2_b"], self.h, res=self.h, out2=hb, name="vit.fc2", stat_partials=self.stat_p[0] if fused else None)
             self._hb_prev = hb
         else:
             self._lin(self.attn_out, v["proj_w"], v["proj_b"], self.h, res=self.h, name="vit.out_proj")

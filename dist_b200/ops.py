@@ -17,6 +17,7 @@ F32, BF16 = 0, 1
 ACT_NONE, ACT_QUICKGELU = 0, 1
 IMPL_AUTO, IMPL_SIMT, IMPL_TCGEN05, IMPL_TCGEN05_1CTA, IMPL_TCGEN05_2CTA = 0, 1, 2, 3, 4
 MAX_TAPS = 9
+STAT_SLOTS = 16
 
 _TORCH2ENUM = {torch.float32: F32, torch.bfloat16: BF16}
 
@@ -38,7 +39,7 @@ class GemmDesc(C.Structure):
         ("ld_out", C.c_int64), ("out_gstride", C.c_int64), ("out_roff", C.c_int64), ("out_rep_stride", C.c_int64),
         ("out2", C.c_void_p), ("out2_dtype", C.c_int32), ("act", C.c_int32),
         ("ld_out2", C.c_int64), ("block_n", C.c_int32), ("group_dim", C.c_int32),
-        ("ln_stats", C.c_void_p), ("ln_wsum", C.c_void_p),
+        ("ln_stats", C.c_void_p), ("ln_wsum", C.c_void_p), ("stat_partials", C.c_void_p),
     ]
 
 
@@ -89,6 +90,7 @@ def lib():
     L.distb200_gemm.argtypes = [C.POINTER(GemmDesc), vp]
     L.distb200_layernorm.argtypes = [vp, i64, vp, i64, i64, i64, i32, f32, vp, vp, vp, i64, vp, vp, vp, i64, i32, vp]
     L.distb200_row_stats.argtypes = [vp, i32, i64, i64, i32, f32, vp, vp]
+    L.distb200_row_stats_finalize.argtypes = [vp, i64, i32, f32, vp, vp]
     L.distb200_attention.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp]
     L.distb200_cross_attention.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp]
     L.distb200_attention_causal.argtypes = [vp, vp, i32, i32, i32, i32, vp]
@@ -117,7 +119,7 @@ def lib():
     for name in TRAIN_EXPORTS:
         getattr(L, name).restype = C.c_int
     for name in ("row_stats", "gemm", "layernorm", "attention", "cross_attention", "patchify", "patchify_u8", "rows_bcast", "mean_rows", "class_head", "view_ensemble",
-                 "topk_correct", "attention_causal", "embed_tokens", "gather_eot"):
+                 "topk_correct", "attention_causal", "embed_tokens", "gather_eot", "row_stats_finalize"):
         getattr(L, "distb200_" + name).restype = C.c_int
     assert L.distb200_version() == 100 and L.distb200_arch() == 100
     _LIB = L
@@ -130,7 +132,8 @@ TRAIN_EXPORTS = ("distb200_gemm_wgrad", "distb200_quickgelu", "distb200_quickgel
 
 EXPORTS = TRAIN_EXPORTS + ("distb200_version", "distb200_arch", "distb200_last_error", "distb200_gemm", "distb200_row_stats", "distb200_layernorm",
            "distb200_attention", "distb200_cross_attention", "distb200_patchify", "distb200_patchify_u8", "distb200_view_ensemble", "distb200_topk_correct", "distb200_rows_bcast",
-           "distb200_mean_rows", "distb200_class_head", "distb200_attention_causal", "distb200_embed_tokens", "distb200_gather_eot")
+           "distb200_mean_rows", "distb200_class_head", "distb200_attention_causal", "distb200_embed_tokens", "distb200_gather_eot",
+           "distb200_row_stats_finalize")
 
 
 class DistB200Error(RuntimeError):
@@ -166,7 +169,7 @@ class Call:
 def gemm(a, b, n, k, *, a_dim=None, a_stride=None, taps=((0, 0, 0),), b_tap_stride=0, ldb=None, img_w=0,
          groups=1, rows_per_group=None, group_dim=2, bias=None, res=None, ld_res=0, res_gstride=0, res_roff=0,
          res_rep_stride=0, out=None, ld_out=0, out_gstride=None, out_roff=0, out_rep=1, out_rep_stride=0,
-         out2=None, ld_out2=0, act=ACT_NONE, impl=IMPL_AUTO, block_n=0, ln_stats=None, ln_wsum=None, name="gemm"):
+         out2=None, ld_out2=0, act=ACT_NONE, impl=IMPL_AUTO, block_n=0, ln_stats=None, ln_wsum=None, stat_partials=None, name="gemm"):
     """Prepare one ``distb200_gemm`` (see the header for the exact definition).
 
     Defaults describe a plain ``out[M, n] = a[M, k] @ b[n, k]^T``: ``a`` is a 2-D row-major tensor,
@@ -210,6 +213,9 @@ def gemm(a, b, n, k, *, a_dim=None, a_stride=None, taps=((0, 0, 0),), b_tap_stri
     d.act, d.ld_out2, d.block_n = int(act), int(ld_out2), int(block_n)
     d.ln_stats, d.ln_wsum = _ptr(ln_stats), _ptr(ln_wsum)
     assert (ln_stats is None) == (ln_wsum is None)
+    d.stat_partials = _ptr(stat_partials)
+    if stat_partials is not None:
+        assert stat_partials.dtype == torch.float32 and stat_partials.numel() >= int(groups) * int(rows_per_group) * STAT_SLOTS * 2
     rows = int(groups) * int(rows_per_group)
     flops = 2 * rows * int(n) * int(k) * len(taps)
     esz = a.element_size()
@@ -220,7 +226,7 @@ def gemm(a, b, n, k, *, a_dim=None, a_stride=None, taps=((0, 0, 0),), b_tap_stri
         nbytes += rows * int(n) * out2.element_size() * int(out_rep)
     if res is not None:
         nbytes += rows * int(n) * 4 * int(out_rep)
-    return Call(lib().distb200_gemm, (C.byref(d),), name, keep=(d, a, b, bias, res, out, out2, ln_stats, ln_wsum), flops=flops, nbytes=nbytes)
+    return Call(lib().distb200_gemm, (C.byref(d),), name, keep=(d, a, b, bias, res, out, out2, ln_stats, ln_wsum, stat_partials), flops=flops, nbytes=nbytes)
 
 
 def layernorm(x, g1, b1, y1, *, in2=None, in2_period=1, g2=None, b2=None, y2=None, rows=None, cols=None,
@@ -246,6 +252,14 @@ def row_stats(x, stats, rows=None, cols=None, ld=None, eps=1e-5, name="row_stats
     assert stats.dtype == torch.float32
     args = (x.data_ptr(), enum_of(x), int(ld if ld is not None else cols), rows, cols, float(eps), stats.data_ptr())
     return Call(lib().distb200_row_stats, args, name, keep=(x, stats), nbytes=rows * cols * x.element_size())
+
+
+def row_stats_finalize(partials, cols, stats, rows=None, eps=1e-5, name="row_stats_finalize"):
+    """(mean, rstd) per row from the slots a GEMM epilogue emitted (``gemm(..., stat_partials=)``)."""
+    rows = int(rows if rows is not None else stats.numel() // 2)
+    assert partials.dtype == stats.dtype == torch.float32 and partials.numel() >= rows * STAT_SLOTS * 2
+    args = (partials.data_ptr(), rows, int(cols), float(eps), stats.data_ptr())
+    return Call(lib().distb200_row_stats_finalize, args, name, keep=(partials, stats), nbytes=rows * (STAT_SLOTS * 8 + 8))
 
 
 def attention(qkv, out, frames, tokens, heads, impl=IMPL_AUTO, name="attention"):

@@ -28,6 +28,7 @@ extern "C" {
 
 #define DISTB200_VERSION 100
 #define DISTB200_MAX_TAPS 9
+#define DISTB200_STAT_SLOTS 16
 
 enum { DISTB200_F32 = 0, DISTB200_BF16 = 1 };
 enum { DISTB200_ACT_NONE = 0, DISTB200_ACT_QUICKGELU = 1 };   /* x * sigmoid(1.702 x), clip.py:199-201 */
@@ -105,6 +106,14 @@ typedef struct distb200_gemm_desc {
      * Both NULL = off.  Needs a bf16 `out` only (no out2 / res / taps). */
     const float* ln_stats;
     const float* ln_wsum;
+    /* Producer side of the folded LayerNorm: when non-NULL, the epilogue also emits, for every output row, the sum and the sum of
+     * squares of the bf16 values it writes to out2 - as DISTB200_STAT_SLOTS float2 slots per row,
+     *     stat_partials[((gi*rows_per_group + r) * DISTB200_STAT_SLOTS + slot) * 2 + {0, 1}],
+     * one slot per (column tile, epilogue warp phase), each written by exactly one warp with plain stores (deterministic; slots
+     * the launch does not own are left untouched, so the buffer starts zeroed and is used by launches of one shape).
+     * distb200_row_stats_finalize reduces the slots to the (mean, rstd) pairs that ln_stats takes: the stand-alone pass over
+     * the bf16 copy (distb200_row_stats) disappears.  Needs fp32 out + bf16 out2 + res, no activation, out_rep == 1, tcgen05. */
+    float* stat_partials;
 } distb200_gemm_desc;
 
 int distb200_gemm(const distb200_gemm_desc* desc, void* stream);
@@ -122,6 +131,10 @@ int distb200_layernorm(const float* in1, int64_t ld_in1, const float* in2, int64
 /* (mean, rstd) of every row of a [rows, cols] matrix (row pitch ld), biased variance + eps as LayerNorm uses them
  * (clip.py:181-187): stats[2*row] = mean, stats[2*row + 1] = 1 / sqrt(var + eps).  Feeds distb200_gemm_desc.ln_stats. */
 int distb200_row_stats(const void* x, int32_t dtype, int64_t ld, int64_t rows, int32_t cols, float eps, float* stats, void* stream);
+
+/* stats[row] = (mean, rstd) from the DISTB200_STAT_SLOTS (sum, sum of squares) slots per row that distb200_gemm emitted
+ * (distb200_gemm_desc.stat_partials), summed in slot order: mean = S/cols, rstd = 1/sqrt(max(Q/cols - mean^2, 0) + eps). */
+int distb200_row_stats_finalize(const float* stat_partials, int64_t rows, int32_t cols, float eps, float* stats, void* stream);
 
 /* Multi-head self attention over the N tokens of each frame, head dim 64, no mask
  * (nn.MultiheadAttention inside ResidualAttentionBlockMid, clip.py:155,166-168).

@@ -303,3 +303,33 @@ def test_gemm_with_folded_layernorm(M, N, K, gelu, impl):
     if gelu:
         ref = _qgelu(ref)
     assert rel_l2(out, ref) < 6e-3                              # bf16 weights (gamma folded) and bf16 output
+
+
+@pytest.mark.parametrize("M,N,K", [(1000, 768, 768), (777, 768, 3072), (300, 1024, 1024), (130, 384, 128), (50432, 768, 768)])
+@pytest.mark.parametrize("impl", [0, 3])               # IMPL_AUTO (CTA pairs when the grid is large enough), IMPL_TCGEN05_1CTA
+def test_gemm_emits_row_statistics(M, N, K, impl):
+    """distb200_gemm_desc.stat_partials + distb200_row_stats_finalize: (mean, rstd) of exactly the bf16 rows written to out2,
+    next to the unchanged fp32 / bf16 outputs; a second launch into the same slots gives the same bits (plain stores, no atomics)."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(M + N)
+    a = (torch.randn(M, K, generator=g) / K ** 0.5).to(torch.bfloat16).to(DEV)
+    w = torch.randn(N, K, generator=g).to(torch.bfloat16).to(DEV)
+    bias = torch.randn(N, generator=g).to(DEV)
+    res = (3.0 * torch.randn(M, N, generator=g) + 1.5).to(DEV)        # a non-zero row mean: exercises the one-pass variance
+    plain, plain_b = res.clone(), torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+    _run(ops.gemm(a, w, N, K, bias=bias, res=plain, ld_res=N, out=plain, ld_out=N, out2=plain_b, ld_out2=N, impl=impl))
+    out, out_b = res.clone(), torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+    parts = torch.zeros(M, ops.STAT_SLOTS, 2, device=DEV)
+    stats = torch.empty(M, 2, device=DEV)
+    call = ops.gemm(a, w, N, K, bias=bias, res=out, ld_res=N, out=out, ld_out=N, out2=out_b, ld_out2=N, stat_partials=parts, impl=impl)
+    _run(call)
+    _run(ops.row_stats_finalize(parts, N, stats))
+    assert torch.equal(out, plain) and torch.equal(out_b, plain_b)
+    xd = out_b.double()
+    mu, var = xd.mean(dim=1), xd.var(dim=1, unbiased=False)
+    assert rel_l2(stats[:, 0], mu) < 1e-5, rel_l2(stats[:, 0], mu)
+    assert rel_l2(stats[:, 1], (var + 1e-5).rsqrt()) < 2e-5, rel_l2(stats[:, 1], (var + 1e-5).rsqrt())
+    first = parts.clone()
+    out.copy_(res)
+    _run(call)
+    assert torch.equal(parts, first)
