@@ -600,6 +600,19 @@ int gemm_tcgen05_launch(const distb200_gemm_desc& d, cudaStream_t stream) {
     args.d = d;
     args.group_dim = d.group_dim == 3 ? 3 : 2;
     args.block_n = d.block_n > 0 ? d.block_n : pick_block_n(d.n);
+    if (d.block_n == 0 && d.img_w == 0 && d.impl != DISTB200_IMPL_TCGEN05_2CTA && !d.stat_partials) {
+        // Few-row GEMMs (the ada-pooling head: 32 ... 256 rows) would occupy a handful of SMs, each walking the whole reduction
+        // alone: narrower column tiles spread the weight matrix over more SMs (the operand re-reads stay in L2).
+        const long long row_tiles0 = d.groups * ((d.rows_per_group + BLOCK_M - 1) / BLOCK_M);
+        static const int narrow_env = getenv("DISTB200_GEMM_NARROW") ? atoi(getenv("DISTB200_GEMM_NARROW")) : 1;
+        if (narrow_env && row_tiles0 * ((d.n + args.block_n - 1) / args.block_n) * 4 <= sm_count()) {
+            for (int bn = args.block_n - 16; bn >= 16; bn -= 16) {
+                if (d.n % bn) continue;
+                args.block_n = bn;
+                if (row_tiles0 * (d.n / bn) >= sm_count()) break;
+            }
+        }
+    }
     DISTB200_REQUIRE(args.block_n % 16 == 0 && args.block_n >= 16 && args.block_n <= 256, "gemm(tcgen05): block_n=%d", args.block_n);
     args.k_blocks = (d.k + BLOCK_K - 1) / BLOCK_K;
     if (d.img_w > 0) {

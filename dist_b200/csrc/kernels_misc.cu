@@ -446,7 +446,7 @@ __global__ void __launch_bounds__(128) cross_attention_kernel(const T* __restric
 // ---------------------------------------------------------------------------------------------------
 // class head: one block per clip.
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) class_head_kernel(const float* __restrict__ emb, const float* __restrict__ text_n, float scale,
+__global__ void __launch_bounds__(1024) class_head_kernel(const float* __restrict__ emb, const float* __restrict__ text_n, float scale,
                                                          int E, int C, float* logits, float* probs) {
     grid_dep_sync();
     extern __shared__ float sh[];          // [E] embedding, [C] logits, [32] scratch
@@ -468,9 +468,16 @@ __global__ void __launch_bounds__(256) class_head_kernel(const float* __restrict
     const float inv = scale * rsqrtf(tot);
     __syncthreads();
     for (int c = warp; c < C; c += nw) {
-        float dot = 0.f;
-        for (int e = lane; e < E; e += 32) dot = fmaf(se[e], text_n[(long long)c * E + e], dot);
-        dot = warp_sum(dot);
+        // four independent loads in flight per lane: the loop is bound by the latency of the label-embedding reads
+        const float* tr = text_n + (long long)c * E;
+        float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+        int e = lane;
+        for (; e + 96 < E; e += 128) {
+            const float t0 = __ldg(tr + e), t1 = __ldg(tr + e + 32), t2 = __ldg(tr + e + 64), t3 = __ldg(tr + e + 96);
+            d0 = fmaf(se[e], t0, d0); d1 = fmaf(se[e + 32], t1, d1); d2 = fmaf(se[e + 64], t2, d2); d3 = fmaf(se[e + 96], t3, d3);
+        }
+        for (; e < E; e += 32) d0 = fmaf(se[e], __ldg(tr + e), d0);
+        float dot = warp_sum((d0 + d1) + (d2 + d3));
         if (lane == 0) {
             sl[c] = dot * inv;
             if (logits) logits[(long long)b * C + c] = dot * inv;
@@ -794,7 +801,7 @@ extern "C" int distb200_class_head(const float* emb, const float* text_n, float 
     if (batch == 0) return 0;
     const size_t smem = (size_t)(embed_dim + classes + 32) * sizeof(float);
     DISTB200_REQUIRE(smem <= 48 * 1024, "class_head: E + C too large for one block (%zu bytes)", smem);
-    DISTB200_LAUNCH(class_head_kernel, batch, 256, smem, (cudaStream_t)stream, emb, text_n, scale, embed_dim, classes, logits, probs);
+    DISTB200_LAUNCH(class_head_kernel, batch, 1024, smem, (cudaStream_t)stream, emb, text_n, scale, embed_dim, classes, logits, probs);
     return check_launch("class_head");
 }
 

@@ -240,7 +240,7 @@ class DistEngine:
         # +0.03 ms and removes 0.18 ms of row_stats; out_proj is bound by its epilogue / the fp32 stream and loses +0.18 ms for the
         # 0.19 ms it saves.  Hence mode 2 by default (0: stand-alone row_stats, 1: both producers, 2: FC2 only).
         mode = os.environ.get("DISTB200_LN_STATS_FUSED", "2")
-        self.stats_fused = self.ln_fold and mode != "0"
+        self.stats_fused = self.ln_fold and mode != "0" and self.gemm_impl != ops.IMPL_SIMT       # emitted by the tcgen05 epilogue only
         self.stats_fused_out_proj = self.stats_fused and mode != "2"
         if self.ln_fold:
             self.hb_mid = z(Mv, D)
