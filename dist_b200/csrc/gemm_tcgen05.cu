@@ -163,6 +163,7 @@ struct Epi {
             o2 = reinterpret_cast<char*>(d.out2) + ((dst_row0 + sub) * d.ld_out2 + n) * es;
             s2 = 4 * d.ld_out2 * es;
         }
+        const bool act_on = ACT != 0 && n >= d.act_from;          // the activation may cover a column suffix only
         const float4* st4 = reinterpret_cast<const float4*>(stage);
         float4 vv[8];                      // all shared-memory reads first: their latency overlaps instead of serialising
 #pragma unroll
@@ -182,11 +183,11 @@ struct Epi {
             if (RES) {
                 v.x += rv[i].x; v.y += rv[i].y; v.z += rv[i].z; v.w += rv[i].w;
             }
-            if (ACT == 1) {
+            if (ACT == 1 && act_on) {
                 quick_gelu_pair_fast(v.x, v.y);
                 quick_gelu_pair_fast(v.z, v.w);
             }
-            if (ACT == 2) {
+            if (ACT == 2 && act_on) {
                 v.x = quick_gelu_precise(v.x); v.y = quick_gelu_precise(v.y);
                 v.z = quick_gelu_precise(v.z); v.w = quick_gelu_precise(v.w);
             }
@@ -590,6 +591,7 @@ int gemm_tcgen05_launch(const distb200_gemm_desc& d, cudaStream_t stream) {
                         "gemm(tcgen05): ln_stats / ln_wsum alignment");
     }
 
+    DISTB200_REQUIRE(d.act_from >= 0 && d.act_from % 4 == 0, "gemm(tcgen05): act_from=%d must be a non-negative multiple of 4", d.act_from);
     if (d.stat_partials) {
         DISTB200_REQUIRE(d.out && d.out_dtype == DISTB200_F32 && d.out2 && d.out2_dtype == DISTB200_BF16 && d.res && d.act == DISTB200_ACT_NONE &&
                         d.out_rep == 1 && !d.ln_stats, "gemm(tcgen05): stat_partials needs fp32 out + bf16 out2 + res, no activation, out_rep 1");

@@ -141,29 +141,33 @@ __device__ __forceinline__ void load_row8(const bf16* p, float* v) {
 // ---------------------------------------------------------------------------------------------------
 // row statistics for the LayerNorm folded into a GEMM: one warp per row, the row in registers, two-pass variance
 // ---------------------------------------------------------------------------------------------------
-template <typename T, int V>
+// LPR lanes per row (32, or 16 for rows of <= 512 values so that a warp covers two rows), V 16-byte pieces per lane.
+template <typename T, int V, int LPR>
 __global__ void __launch_bounds__(256) row_stats_kernel(const T* __restrict__ x, long long ld, long long rows, int cols, float eps, float2* stats) {
     grid_dep_sync();
-    const int lane = threadIdx.x & 31;
-    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (row >= rows) return;
-    const T* p = x + row * ld;
+    constexpr int RPW = 32 / LPR;
+    const int lane = threadIdx.x & 31, sub = lane % LPR;
+    const long long row = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW + lane / LPR;
+    const bool ok = row < rows;
+    const T* p = x + (ok ? row : rows - 1) * ld;
     float v[8 * V];                      // 8 consecutive values (16 bytes of bf16) per lane and step
     float sum = 0.f;
 #pragma unroll
     for (int i = 0; i < V; ++i) {
-        const int c = (i * 32 + lane) * 8;
+        const int c = (i * LPR + sub) * 8;
         if (c < cols) {
             load_row8(p + c, v + 8 * i);
 #pragma unroll
             for (int j = 0; j < 8; ++j) sum += v[8 * i + j];
         }
     }
-    const float mean = warp_sum(sum) / (float)cols;
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum / (float)cols;
     float sq = 0.f;
 #pragma unroll
     for (int i = 0; i < V; ++i) {
-        const int c = (i * 32 + lane) * 8;
+        const int c = (i * LPR + sub) * 8;
         if (c < cols)
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -171,8 +175,9 @@ __global__ void __launch_bounds__(256) row_stats_kernel(const T* __restrict__ x,
                 sq += dlt * dlt;
             }
     }
-    const float var = warp_sum(sq) / (float)cols;
-    if (lane == 0) stats[row] = make_float2(mean, rsqrtf(var + eps));
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    if (ok && sub == 0) stats[row] = make_float2(mean, rsqrtf(sq / (float)cols + eps));
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -335,7 +340,7 @@ __global__ void zero_pad_cols_kernel(OutT* out, long long rows, int c0, long lon
 
 // ---------------------------------------------------------------------------------------------------
 __global__ void rows_bcast_kernel(float* dst, long long row_stride, long long n_rows, int cols, const float* __restrict__ table,
-                                  long long period, int accumulate) {
+                                  long long period, int accumulate, bf16* dst2, long long row_stride2) {
     grid_dep_sync();
     const long long total = n_rows * cols;
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
@@ -343,7 +348,9 @@ __global__ void rows_bcast_kernel(float* dst, long long row_stride, long long n_
         const int c = (int)(idx % cols);
         const float t = table[(i % period) * cols + c];
         float* p = dst + i * row_stride + c;
-        *p = accumulate ? *p + t : t;
+        const float v = accumulate ? *p + t : t;
+        *p = v;
+        if (dst2) dst2[i * row_stride2 + c] = __float2bfloat16_rn(v);
     }
 }
 
@@ -666,12 +673,12 @@ extern "C" int distb200_row_stats(const void* x, int32_t dtype, int64_t ld, int6
     DISTB200_REQUIRE(x && stats, "row_stats: null pointer");
     DISTB200_REQUIRE(cols % 8 == 0 && cols <= 1024 && ld % 8 == 0, "row_stats: cols=%d must be a multiple of 8 and <= 1024 (ld %% 8 == 0)", cols);
     DISTB200_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(stats) & 7) == 0, "row_stats: alignment");
-    const unsigned grid = (unsigned)((rows + 7) / 8);
-#define DISTB200_RS(T, V) DISTB200_LAUNCH((row_stats_kernel<T, V>), grid, 256, 0, stream, (const T*)x, ld, rows, cols, eps, (float2*)stats)
+#define DISTB200_RS(T, V, LPR) DISTB200_LAUNCH((row_stats_kernel<T, V, LPR>), (unsigned)((rows + 8 * (32 / LPR) - 1) / (8 * (32 / LPR))), 256, 0, stream, \
+                                               (const T*)x, ld, rows, cols, eps, (float2*)stats)
     if (dtype == DISTB200_F32) {
-        if (cols <= 256) DISTB200_RS(float, 1); else if (cols <= 512) DISTB200_RS(float, 2); else if (cols <= 768) DISTB200_RS(float, 3); else DISTB200_RS(float, 4);
+        if (cols <= 256) DISTB200_RS(float, 2, 16); else if (cols <= 512) DISTB200_RS(float, 4, 16); else if (cols <= 768) DISTB200_RS(float, 3, 32); else DISTB200_RS(float, 4, 32);
     } else {
-        if (cols <= 256) DISTB200_RS(bf16, 1); else if (cols <= 512) DISTB200_RS(bf16, 2); else if (cols <= 768) DISTB200_RS(bf16, 3); else DISTB200_RS(bf16, 4);
+        if (cols <= 256) DISTB200_RS(bf16, 2, 16); else if (cols <= 512) DISTB200_RS(bf16, 4, 16); else if (cols <= 768) DISTB200_RS(bf16, 3, 32); else DISTB200_RS(bf16, 4, 32);
     }
 #undef DISTB200_RS
     return check_launch("row_stats");
@@ -765,10 +772,11 @@ extern "C" int distb200_topk_correct(const float* video_preds, const int64_t* vi
 }
 
 extern "C" int distb200_rows_bcast(float* dst, int64_t row_stride, int64_t n_rows, int32_t cols, const float* table, int64_t period,
-                                   int32_t accumulate, void* stream) {
+                                   int32_t accumulate, void* dst2_bf16, int64_t row_stride2, void* stream) {
     if (n_rows == 0 || cols == 0) return 0;
     DISTB200_REQUIRE(period >= 1, "rows_bcast: period must be >= 1");
-    DISTB200_LAUNCH(rows_bcast_kernel, grid_for(n_rows * cols, 256), 256, 0, (cudaStream_t)stream, dst, row_stride, n_rows, cols, table, period, accumulate);
+    DISTB200_LAUNCH(rows_bcast_kernel, grid_for(n_rows * cols, 256), 256, 0, (cudaStream_t)stream, dst, row_stride, n_rows, cols, table, period, accumulate,
+                    (bf16*)dst2_bf16, (long long)row_stride2);
     return check_launch("rows_bcast");
 }
 

@@ -148,6 +148,18 @@ class PackedWeights:
                 tf1_w=op(sd[it + "temporal_ffn.c_fc1.weight"].float()[:, :, 0, 0, 0]), tf1_b=f32(sd[it + "temporal_ffn.c_fc1.bias"]),
                 tf2_w=op(wk), tf2_b=f32(sd[it + "temporal_ffn.c_fc2.bias"]),
             ))
+            # IntegrationNetwork with both LayerNorms folded (bf16 path): ONE GEMM on the raw rows of `upd` produces
+            # [temporal_ffn.c_fc1(LN_t x) | ffn.c_fc(LN x)] - operand rows [W_tf1 * gamma_t ; W_fc * gamma], their row sums
+            # (of the rounded operand) and the biases W beta + b; QuickGELU covers the ffn columns only (dist.py:40-45)
+            wt = sd[it + "temporal_ffn.c_fc1.weight"].detach().double()[:, :, 0, 0, 0]
+            wf = sd[it + "ffn.c_fc.weight"].detach().double()
+            g1, b1 = sd[it + "ln.weight"].detach().double(), sd[it + "ln.bias"].detach().double()
+            g2, b2 = sd[it + "ln_temporal.weight"].detach().double(), sd[it + "ln_temporal.bias"].detach().double()
+            cat = torch.cat([wt * g2[None, :], wf * g1[None, :]], dim=0).float().to(device=device).to(act_dtype).contiguous()
+            self.dist[-1].update(
+                int_wf=cat, int_ws=cat.float().sum(dim=1).contiguous(),
+                int_bf=f32(torch.cat([wt @ b2 + sd[it + "temporal_ffn.c_fc1.bias"].detach().double(),
+                                      wf @ b1 + sd[it + "ffn.c_fc.bias"].detach().double()])))
         self.ada = []
         for j in range(a.ada_layers):
             pre = "dist_net.adapooling_nets.%d." % j
@@ -258,6 +270,13 @@ class DistEngine:
         self.int_a1 = z(Mv, Ci)
         self.int_a2 = z(Mv, Ci)
         self.int_h = z(Mv, a.integration_hidden + a.integration_temporal_hidden)     # [ffn hidden | temporal hidden]
+        # folded IntegrationNetwork (bf16 path): bf16 copy of `upd`, its row statistics, and one wide activation buffer
+        # [temporal c_fc1 output | ffn hidden | temporal hidden] so that every consumer reads a column slice of it
+        self.int_fold = self.ln_fold and os.environ.get("DISTB200_INT_FOLD", "1") != "0"
+        if self.int_fold:
+            self.upd_a = z(Mv, Ci)
+            self.int_st = z(Mv, 2, dtype=f32)
+            self.int_w = z(Mv, 2 * a.integration_temporal_hidden + a.integration_hidden)
         self.tf1 = z(Mv, a.integration_temporal_hidden)
         self.kv_s = z(Mv, 2 * Ci)
         self.sp = z(F, Ci, dtype=f32)
@@ -437,8 +456,10 @@ class DistEngine:
         self._gemm(self.xT_a, d["t2i_w"], Ci, Ct, a_dim=(Ct, P, al, F), a_stride=(1, Ct, P * Ct, al * P * Ct), group_dim=3,
                    taps=[(0, k, 0) for k in range(al)], b_tap_stride=Ci * Ct, ldb=Ct, groups=F, rows_per_group=P,
                    bias=d["t2i_b"], res=self.mid, ld_res=Ci, res_gstride=N, res_roff=1,
-                   out=self.mid, ld_out=Ci, out_gstride=N, out_roff=1, name="dist.t2i")
-        add(ops.rows_bcast(self.mid, N * Ci, F, Ci, d["t2i_cls"], t, True, name="dist.t2i.cls"))
+                   out=self.mid, ld_out=Ci, out_gstride=N, out_roff=1, out2=self.upd_a if self.int_fold else None, ld_out2=Ci,
+                   name="dist.t2i")
+        add(ops.rows_bcast(self.mid, N * Ci, F, Ci, d["t2i_cls"], t, True, dst2=self.upd_a if self.int_fold else None, row_stride2=N * Ci,
+                           name="dist.t2i.cls"))
 
         # ---- integration -> temporal (dist.py:90-105,231): patch tokens only, nearest upsample = row replication
         # (the fused temporal stream of the LAST layer is read by nothing, dist.py:231-235: its branch is skipped)
@@ -448,6 +469,18 @@ class DistEngine:
                        res_rep_stride=P, out=self.xT, ld_out=Ct, out_gstride=al * P, out_rep=al, out_rep_stride=P, name="dist.i2t")
 
         # ---- IntegrationNetwork (dist.py:16-45) on upd = mid ----
+        if self.int_fold:
+            # both LayerNorms folded into one GEMM over the bf16 copy of upd (written by the t2i epilogue and the cls-token kernel)
+            Ih, wide = a.integration_hidden, 2 * Cm + a.integration_hidden
+            add(ops.row_stats(self.upd_a, self.int_st, name="dist.int.stats"))
+            self._gemm(self.upd_a, d["int_wf"], Cm + Ih, Ci, bias=d["int_bf"], out=self.int_w, ld_out=wide, act=ops.ACT_QUICKGELU, act_from=Cm,
+                       ln_stats=self.int_st, ln_wsum=d["int_ws"], name="dist.int.fc")
+            self._gemm(self.int_w, d["tf2_w"], Cm, Cm, a_dim=(Cm, t * N, b, 1), a_stride=(1, wide, t * N * wide, Mv * wide),
+                       taps=[((k - half) * N, 0, 0) for k in range(a.t_kernel)], b_tap_stride=Cm * Cm, ldb=Cm,
+                       groups=b, rows_per_group=t * N, bias=d["tf2_b"], out=self.int_w[:, Cm + Ih:], ld_out=wide, act=ops.ACT_QUICKGELU,
+                       name="dist.int.t_conv")
+            self._lin(self.int_w[:, Cm:], d["prj_w"], d["prj_b"], self.res, name="dist.int.proj")
+            return
         add(ops.layernorm(self.mid, d["ln"][0], d["ln"][1], self.int_a1, g2=d["ln_t"][0], b2=d["ln_t"][1], y2=self.int_a2,
                           name="dist.int.ln"))
         Ih = a.integration_hidden

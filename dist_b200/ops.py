@@ -40,6 +40,7 @@ class GemmDesc(C.Structure):
         ("out2", C.c_void_p), ("out2_dtype", C.c_int32), ("act", C.c_int32),
         ("ld_out2", C.c_int64), ("block_n", C.c_int32), ("group_dim", C.c_int32),
         ("ln_stats", C.c_void_p), ("ln_wsum", C.c_void_p), ("stat_partials", C.c_void_p),
+        ("act_from", C.c_int32), ("reserved0", C.c_int32),
     ]
 
 
@@ -100,7 +101,7 @@ def lib():
     L.distb200_patchify_u8.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i64, i32, C.POINTER(C.c_float * 3), C.POINTER(C.c_float * 3), vp]
     L.distb200_view_ensemble.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, i64, vp]
     L.distb200_topk_correct.argtypes = [vp, vp, i64, i32, vp, i32, vp, vp]
-    L.distb200_rows_bcast.argtypes = [vp, i64, i64, i32, vp, i64, i32, vp]
+    L.distb200_rows_bcast.argtypes = [vp, i64, i64, i32, vp, i64, i32, vp, i64, vp]
     L.distb200_mean_rows.argtypes = [vp, i64, i32, i64, i32, vp, i32, vp]
     L.distb200_class_head.argtypes = [vp, vp, f32, i32, i32, i32, vp, vp, vp]
     # fine-tuning step
@@ -169,7 +170,7 @@ class Call:
 def gemm(a, b, n, k, *, a_dim=None, a_stride=None, taps=((0, 0, 0),), b_tap_stride=0, ldb=None, img_w=0,
          groups=1, rows_per_group=None, group_dim=2, bias=None, res=None, ld_res=0, res_gstride=0, res_roff=0,
          res_rep_stride=0, out=None, ld_out=0, out_gstride=None, out_roff=0, out_rep=1, out_rep_stride=0,
-         out2=None, ld_out2=0, act=ACT_NONE, impl=IMPL_AUTO, block_n=0, ln_stats=None, ln_wsum=None, stat_partials=None, name="gemm"):
+         out2=None, ld_out2=0, act=ACT_NONE, impl=IMPL_AUTO, block_n=0, ln_stats=None, ln_wsum=None, stat_partials=None, act_from=0, name="gemm"):
     """Prepare one ``distb200_gemm`` (see the header for the exact definition).
 
     Defaults describe a plain ``out[M, n] = a[M, k] @ b[n, k]^T``: ``a`` is a 2-D row-major tensor,
@@ -214,6 +215,7 @@ def gemm(a, b, n, k, *, a_dim=None, a_stride=None, taps=((0, 0, 0),), b_tap_stri
     d.ln_stats, d.ln_wsum = _ptr(ln_stats), _ptr(ln_wsum)
     assert (ln_stats is None) == (ln_wsum is None)
     d.stat_partials = _ptr(stat_partials)
+    d.act_from = int(act_from)
     if stat_partials is not None:
         assert stat_partials.dtype == torch.float32 and stat_partials.numel() >= int(groups) * int(rows_per_group) * STAT_SLOTS * 2
     rows = int(groups) * int(rows_per_group)
@@ -336,10 +338,12 @@ def topk_correct(video_preds, video_labels, ks_dev, correct, stream):
                                        correct.data_ptr(), stream), "topk_correct")
 
 
-def rows_bcast(dst, row_stride, n_rows, cols, table, period, accumulate, name="rows_bcast"):
+def rows_bcast(dst, row_stride, n_rows, cols, table, period, accumulate, dst2=None, row_stride2=0, name="rows_bcast"):
     assert dst.dtype == torch.float32 and table.dtype == torch.float32
-    args = (dst.data_ptr(), int(row_stride), int(n_rows), int(cols), table.data_ptr(), int(period), int(bool(accumulate)))
-    return Call(lib().distb200_rows_bcast, args, name, keep=(dst, table), nbytes=n_rows * cols * 8)
+    assert dst2 is None or dst2.dtype == torch.bfloat16
+    args = (dst.data_ptr(), int(row_stride), int(n_rows), int(cols), table.data_ptr(), int(period), int(bool(accumulate)),
+            _ptr(dst2), int(row_stride2))
+    return Call(lib().distb200_rows_bcast, args, name, keep=(dst, table, dst2), nbytes=n_rows * cols * 8)
 
 
 def mean_rows(src, row_stride, count, batch, cols, out, name="mean_rows"):

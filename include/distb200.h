@@ -114,6 +114,10 @@ typedef struct distb200_gemm_desc {
      * distb200_row_stats_finalize reduces the slots to the (mean, rstd) pairs that ln_stats takes: the stand-alone pass over
      * the bf16 copy (distb200_row_stats) disappears.  Needs fp32 out + bf16 out2 + res, no activation, out_rep == 1, tcgen05. */
     float* stat_partials;
+    /* The activation applies to the output columns n >= act_from only (0 = every column): lets one GEMM produce an activated and
+     * a linear block side by side (IntegrationNetwork: temporal_ffn.c_fc1 | QuickGELU(ffn.c_fc), dist.py:40-45). */
+    int32_t act_from;
+    int32_t reserved0;
 } distb200_gemm_desc;
 
 int distb200_gemm(const distb200_gemm_desc* desc, void* stream);
@@ -179,9 +183,10 @@ int distb200_patchify_u8(const uint8_t* frames, void* out, int32_t clips, int32_
                          const float* mean3, const float* std3, void* stream);
 
 /* dst[i*row_stride + c] = (accumulate ? dst[...] : 0) + table[(i % period)*cols + c], i < n_rows (fp32).
- * Class-token rows (clip.py:274), per-frame cls tokens of dist.py:84, broadcast of the aggregated tokens (dist.py:237-238). */
+ * Class-token rows (clip.py:274), per-frame cls tokens of dist.py:84, broadcast of the aggregated tokens (dist.py:237-238).
+ * dst2_bf16 (optional): a bf16 copy of the resulting rows at row pitch row_stride2 (the GEMM operand copy of the stream). */
 int distb200_rows_bcast(float* dst, int64_t row_stride, int64_t n_rows, int32_t cols, const float* table,
-                        int64_t period, int32_t accumulate, void* stream);
+                        int64_t period, int32_t accumulate, void* dst2_bf16, int64_t row_stride2, void* stream);
 
 /* out[b, :] = mean_i src[(b*count + i)*row_stride + :], i < count  (dist.py:243 mean over the sparse frames). */
 int distb200_mean_rows(const float* src, int64_t row_stride, int32_t count, int64_t batch, int32_t cols,

@@ -333,3 +333,29 @@ def test_gemm_emits_row_statistics(M, N, K, impl):
     out.copy_(res)
     _run(call)
     assert torch.equal(parts, first)
+
+
+@pytest.mark.parametrize("impl", ["tcgen05", "simt"])
+def test_gemm_activation_on_a_column_suffix_and_bcast_copy(impl):
+    """distb200_gemm_desc.act_from: QuickGELU on the columns n >= act_from only (folded IntegrationNetwork: linear temporal
+    block | activated ffn block out of one GEMM); rows_bcast's optional bf16 copy of the rows it produced."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(5)
+    M, N, K, cut = 333, 480, 384, 96
+    a = (torch.randn(M, K, generator=g) / K ** 0.5).to(torch.bfloat16).to(DEV)
+    w = torch.randn(N, K, generator=g).to(torch.bfloat16).to(DEV)
+    bias = torch.randn(N, generator=g).to(DEV)
+    wide = torch.zeros(M, 576, device=DEV, dtype=torch.bfloat16)
+    _run(ops.gemm(a, w, N, K, bias=bias, out=wide, ld_out=576, act=ops.ACT_QUICKGELU, act_from=cut,
+                  impl=ops.IMPL_SIMT if impl == "simt" else ops.IMPL_AUTO))
+    ref = a.double() @ w.double().t() + bias.double()
+    ref[:, cut:] = _qgelu(ref[:, cut:])
+    assert rel_l2(wide[:, :cut], ref[:, :cut]) < 4e-3 and rel_l2(wide[:, cut:N], ref[:, cut:]) < 6e-3
+    assert float(wide[:, N:].abs().max()) == 0.0
+    dst = torch.randn(10, 5 * 16, generator=g).to(DEV)
+    want = dst.clone()
+    table = torch.randn(4, 16, generator=g).to(DEV)
+    copy = torch.zeros(10, 5 * 16, device=DEV, dtype=torch.bfloat16)
+    _run(ops.rows_bcast(dst, 5 * 16, 10, 16, table, 4, True, dst2=copy, row_stride2=5 * 16))
+    want[:, :16] += table[torch.arange(10) % 4]
+    assert torch.equal(dst, want) and torch.equal(copy[:, :16], want[:, :16].to(torch.bfloat16)) and float(copy[:, 16:].abs().max()) == 0.0
