@@ -183,7 +183,7 @@ def family(call):
         return "patchify"
     if "attention" in n or n.endswith(".attn"):
         return "attention" if n.startswith("vit") else "cross_attention"
-    if n.endswith((".ln", ".ln_1", ".ln_2", ".ln_pre", ".ln_kv", ".ln_q", ".ln_out", "ln_post")) or ".ln" in n:
+    if n.endswith((".ln", ".ln_1", ".ln_2", ".ln_pre", ".ln_kv", ".ln_q", ".ln_out", "ln_post", ".stats")) or ".ln" in n:
         return "layernorm"
     if "cls" in n and ("rows" in n or n.endswith(".cls")) or n.startswith("ada.init"):
         return "rows_bcast"

@@ -14,8 +14,8 @@ python bench.py --mode train --workload b16_16x32 --steps 10 --warmup 3 > $O/ben
 python tools/profile_train.py --out $O/plan_train_b16_16x32.txt > /dev/null 2>&1
 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file $O/launches.csv \
     python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline > /dev/null 2>&1
-# full-set capture of the first ViT layer and the first DiST layer (launches 5..23 of the plan)
-ncu --set full --clock-control none --import-source on --profile-from-start off --launch-skip 5 -c 19 -o /tmp/layer0 -f \
+# full-set capture of the first ViT layer and the first DiST layer (launches 5..22 of the plan)
+ncu --set full --clock-control none --import-source on --profile-from-start off --launch-skip 5 -c 18 -o /tmp/layer0 -f \
     python tools/run_once.py > /dev/null 2>&1
 ncu -i /tmp/layer0.ncu-rep --page raw --csv > $O/layer0_raw.csv 2>/dev/null
 ls -la $O
