@@ -106,8 +106,14 @@ __global__ void __launch_bounds__(NT) gemm_simt_kernel(const SimtArgs args) {
                     else reinterpret_cast<bf16*>(d.out)[dst * d.ld_out + n] = __float2bfloat16_rn(v);
                 }
                 if (d.out2) {
-                    if (d.out2_dtype == DISTB200_F32) reinterpret_cast<float*>(d.out2)[dst * d.ld_out2 + n] = v;
-                    else reinterpret_cast<bf16*>(d.out2)[dst * d.ld_out2 + n] = __float2bfloat16_rn(v);
+                    long long dst2 = dst;
+                    int n2 = n;
+                    if (d.out2_gdiv > 0) {
+                        dst2 = (ogi / d.out2_gdiv) * d.out2_gstride + d.out2_roff + orr;
+                        n2 = n + (int)(ogi % d.out2_gdiv) * d.out2_cstep;
+                    }
+                    if (d.out2_dtype == DISTB200_F32) reinterpret_cast<float*>(d.out2)[dst2 * d.ld_out2 + n2] = v;
+                    else reinterpret_cast<bf16*>(d.out2)[dst2 * d.ld_out2 + n2] = __float2bfloat16_rn(v);
                 }
             }
         }

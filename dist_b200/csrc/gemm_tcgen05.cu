@@ -146,7 +146,8 @@ struct Epi {
 
     template <bool FULL>
     static __device__ __forceinline__ void finish_rows(const distb200_gemm_desc& d, const float* stage, const float4* rv, const float4 bias,
-                                                       const float4 ws, int lane, int n, int rows_here, long long dst_row0, float2* st) {
+                                                       const float4 ws, int lane, int n, int rows_here, long long dst_row0, float2* st,
+                                                       long long dst2_row0, int col2) {
         const int sub = lane >> 3, chunk = lane & 7;
         char* o1 = nullptr;
         char* o2 = nullptr;
@@ -160,7 +161,7 @@ struct Epi {
         const bool f32_2 = OUT == 3 && d.out2_dtype == DISTB200_F32;
         if (OUT == 2 || (OUT == 3 && d.out2)) {
             const int es = f32_2 ? 4 : 2;
-            o2 = reinterpret_cast<char*>(d.out2) + ((dst_row0 + sub) * d.ld_out2 + n) * es;
+            o2 = reinterpret_cast<char*>(d.out2) + ((dst2_row0 + sub) * d.ld_out2 + n + col2) * es;
             s2 = 4 * d.ld_out2 * es;
         }
         const bool act_on = ACT != 0 && n >= d.act_from;          // the activation may cover a column suffix only
@@ -216,16 +217,17 @@ struct Epi {
     }
 
     static __device__ __forceinline__ void finish(const distb200_gemm_desc& d, const float* stage, const float4* rv, const float4 bias,
-                                                  const float4 ws, int lane, int n, int rows_here, long long dst_row0, float2* st) {
-        if (rows_here >= 32) finish_rows<true>(d, stage, rv, bias, ws, lane, n, rows_here, dst_row0, st);
-        else finish_rows<false>(d, stage, rv, bias, ws, lane, n, rows_here, dst_row0, st);
+                                                  const float4 ws, int lane, int n, int rows_here, long long dst_row0, float2* st,
+                                                  long long dst2_row0, int col2) {
+        if (rows_here >= 32) finish_rows<true>(d, stage, rv, bias, ws, lane, n, rows_here, dst_row0, st, dst2_row0, col2);
+        else finish_rows<false>(d, stage, rv, bias, ws, lane, n, rows_here, dst_row0, st, dst2_row0, col2);
     }
 };
 
 // Per-tile quantities of one epilogue warp.
 struct EpiTile {
-    long long dst0, res0, srow0;
-    int n0, ncols, rows_valid;
+    long long dst0, res0, srow0, dst2_0;
+    int n0, ncols, rows_valid, col2;
 };
 
 __device__ __forceinline__ EpiTile epi_tile(const TcArgs& args, long long tile, int rank, int quad) {
@@ -239,6 +241,13 @@ __device__ __forceinline__ EpiTile epi_tile(const TcArgs& args, long long tile, 
     t.dst0 = tc.gi * d.out_gstride + d.out_roff + r;
     t.res0 = tc.gi * d.res_gstride + d.res_roff + r;
     t.srow0 = tc.gi * d.rows_per_group + r;            // row of the logical A matrix (index of ln_stats)
+    t.dst2_0 = t.dst0;                                 // out2 follows out unless it is placed independently (out2_gdiv)
+    t.col2 = 0;
+    if (d.out2_gdiv > 0) {
+        const uint32_t q = (uint32_t)tc.gi / (uint32_t)d.out2_gdiv;
+        t.dst2_0 = (long long)q * d.out2_gstride + d.out2_roff + r;
+        t.col2 = (int)((uint32_t)tc.gi - q * (uint32_t)d.out2_gdiv) * d.out2_cstep;
+    }
     t.n0 = tc.n0;
     t.ncols = min(args.block_n, d.n - tc.n0);
     return t;
@@ -309,7 +318,8 @@ __device__ __forceinline__ void epilogue_role(const TcArgs& args, uint32_t tmem_
                 __syncwarp();
                 for (int rep = 0; rep < d.out_rep; ++rep) {
                     if (rep > 0) E::prefetch(d, rv, bias, ws, cur.res0 + (long long)rep * d.res_rep_stride, cur.srow0, n, sub, cur.rows_valid, col_ok);
-                    if (col_ok) E::finish(d, stage, rv, bias, ws, lane, n, cur.rows_valid, cur.dst0 + (long long)rep * d.out_rep_stride, st);
+                    if (col_ok) E::finish(d, stage, rv, bias, ws, lane, n, cur.rows_valid, cur.dst0 + (long long)rep * d.out_rep_stride, st,
+                                          cur.dst2_0 + (long long)rep * d.out_rep_stride, cur.col2);
                 }
                 __syncwarp();
             }
@@ -591,6 +601,8 @@ int gemm_tcgen05_launch(const distb200_gemm_desc& d, cudaStream_t stream) {
                         "gemm(tcgen05): ln_stats / ln_wsum alignment");
     }
 
+    DISTB200_REQUIRE(d.out2_gdiv >= 0 && (d.out2_gdiv == 0 || (d.out2 && d.out_rep == 1 && d.out2_cstep % 8 == 0 && d.groups < (1ll << 31))),
+                    "gemm(tcgen05): out2_gdiv needs out2, out_rep == 1 and out2_cstep %% 8 == 0");
     DISTB200_REQUIRE(d.act_from >= 0 && d.act_from % 4 == 0, "gemm(tcgen05): act_from=%d must be a non-negative multiple of 4", d.act_from);
     if (d.stat_partials) {
         DISTB200_REQUIRE(d.out && d.out_dtype == DISTB200_F32 && d.out2 && d.out2_dtype == DISTB200_BF16 && d.res && d.act == DISTB200_ACT_NONE &&

@@ -28,6 +28,13 @@ def _pad8(n):
     return (n + 7) // 8 * 8
 
 
+def _onehot_width(arch):
+    """Columns reserved for one-hot(ti) in the K-concatenated operand: at least t, and such that the bf16 `upd` block behind
+    it starts on a 128-byte boundary (64 elements)."""
+    base = arch.width + arch.alpha * arch.temporal_dim
+    return (base + arch.sparse_frames + 63) // 64 * 64 - base
+
+
 def plan_branches(names, sel):
     """Split a planned forward (call names in plan order) into the ViT branch (0) and the DiST branch (1) of the CUDA graph.
 
@@ -156,6 +163,24 @@ class PackedWeights:
             g1, b1 = sd[it + "ln.weight"].detach().double(), sd[it + "ln.bias"].detach().double()
             g2, b2 = sd[it + "ln_temporal.weight"].detach().double(), sd[it + "ln_temporal.bias"].detach().double()
             cat = torch.cat([wt * g2[None, :], wf * g1[None, :]], dim=0).float().to(device=device).to(act_dtype).contiguous()
+            # K-concatenated operands (bf16 path, DistEngine.kcat): columns [tap D | alpha temporal rows | one-hot(ti) | upd Ci]
+            #   mid/upd = [tap | xT pair | e_ti] . [W_in | W_t2i,0 .. W_t2i,alpha-1 | cls_ti - b_t2i]^T + (b_in + b_t2i)   (dist.py:229,80-86,232)
+            #   i2t     = [xT pair | e_ti | upd] . [-W_i2t W_t2i | 0 | W_i2t]^T + (b_i2t - W_i2t b_t2i)   on the patch rows,
+            #             i.e. linear_fuse(mid) with mid = upd - t2i(xT) (dist.py:99-105,231 reads the PRE-fusion mid)
+            oh = _onehot_width(a)
+            w_in = sd["dist_net.input_linears.%d.weight" % i].detach().double().cpu()
+            wt2 = sd[t2i + "linear_fuse.weight"].detach().double().cpu()[:, :, :, 0, 0].permute(2, 0, 1)          # [alpha, Ci, Ct]
+            b_t2 = sd[t2i + "linear_fuse.bias"].detach().double().cpu()
+            cls = sd[t2i + "cls_token"].detach().double().cpu().reshape(a.sparse_frames, Ci)
+            w_t2_flat = torch.cat([wt2[k] for k in range(a.alpha)], dim=1)                                   # [Ci, alpha*Ct]
+            onehot = torch.zeros(Ci, oh, dtype=torch.float64)
+            onehot[:, :a.sparse_frames] = (cls - b_t2[None, :]).t()
+            w_i2 = sd[i2t + "linear_fuse.weight"].detach().double().cpu()                                          # [Ct, Ci]
+            i2_cat = torch.cat([-(w_i2 @ w_t2_flat), torch.zeros(Ct, oh, dtype=torch.float64), w_i2], dim=1)
+            self.dist[-1].update(
+                cat_w=op(torch.cat([w_in, w_t2_flat, onehot], dim=1).float()),
+                cat_b=f32(sd["dist_net.input_linears.%d.bias" % i].detach().double().cpu() + b_t2),
+                i2t_cat_w=op(i2_cat.float()), i2t_cat_b=f32(sd[i2t + "linear_fuse.bias"].detach().double().cpu() - w_i2 @ b_t2))
             self.dist[-1].update(
                 int_wf=cat, int_ws=cat.float().sum(dim=1).contiguous(),
                 int_bf=f32(torch.cat([wt @ b2 + sd[it + "temporal_ffn.c_fc1.bias"].detach().double(),
@@ -242,10 +267,25 @@ class DistEngine:
         self.fc1 = z(Mv, 4 * D)
         # bf16 copies of the ViT block outputs (the taps; with the folded LayerNorm also the next block's GEMM operand).  Two
         # buffers, alternating by layer, so that the DiST layer reading tap l may still run while ViT block l+1 writes its own.
-        self.taps = [z(Mv, D), z(Mv, D)] if self.precision == "bf16" else [self.h, self.h]
+        self.ln_fold = self.precision == "bf16" and os.environ.get("DISTB200_LN_FOLD", "1") != "0"
+        self.int_fold = self.ln_fold and os.environ.get("DISTB200_INT_FOLD", "1") != "0"
+        # K-concatenated DiST operands (see PackedWeights): the tap buffers grow the columns [alpha temporal rows | one-hot(ti) |
+        # bf16 upd]; input_linear + the temporal->integration convolution + the cls token become ONE GEMM, `mid` is written once
+        self.kcat = self.int_fold and os.environ.get("DISTB200_KCAT", "1") != "0"
+        if self.kcat:
+            oh = _onehot_width(a)
+            self.tw_oh = D + a.alpha * Ct
+            self.tw_u = self.tw_oh + oh
+            self.tw = (self.tw_u + Ci + 63) // 64 * 64          # row pitch: whole 128-byte lines
+            self.tapw = [z(Mv, self.tw), z(Mv, self.tw)]
+            frames = torch.arange(F, device=dev)
+            for buf in self.tapw:                      # static one-hot(ti) on the class-token row of every frame
+                buf[frames * N, self.tw_oh + frames % a.sparse_frames] = 1.0
+            self.taps = [buf[:, :D] for buf in self.tapw]
+        else:
+            self.taps = [z(Mv, D), z(Mv, D)] if self.precision == "bf16" else [self.h, self.h]
         self.tap = self.taps[0]
         # LayerNorm folded into the QKV / FC1 GEMMs (bf16 path): bf16 copies of the residual stream + per-row statistics
-        self.ln_fold = self.precision == "bf16" and os.environ.get("DISTB200_LN_FOLD", "1") != "0"
         # ... and the statistics themselves come out of the producing GEMM's epilogue (distb200_gemm_desc.stat_partials) instead of a
         # separate pass over the bf16 copy: one slot buffer per producer shape (FC2 -> ln_1, out_proj -> ln_2)
         # Measured (B/16 8+16f, 32 clips, per step): FC2 is tensor-bound and its epilogue has slack - emitting the statistics costs it
@@ -272,9 +312,8 @@ class DistEngine:
         self.int_h = z(Mv, a.integration_hidden + a.integration_temporal_hidden)     # [ffn hidden | temporal hidden]
         # folded IntegrationNetwork (bf16 path): bf16 copy of `upd`, its row statistics, and one wide activation buffer
         # [temporal c_fc1 output | ffn hidden | temporal hidden] so that every consumer reads a column slice of it
-        self.int_fold = self.ln_fold and os.environ.get("DISTB200_INT_FOLD", "1") != "0"
         if self.int_fold:
-            self.upd_a = z(Mv, Ci)
+            self.upd_a = None if self.kcat else z(Mv, Ci)
             self.int_st = z(Mv, 2, dtype=f32)
             self.int_w = z(Mv, 2 * a.integration_temporal_hidden + a.integration_hidden)
         self.tf1 = z(Mv, a.integration_temporal_hidden)
@@ -300,7 +339,8 @@ class DistEngine:
     def _lin(self, a, w, bias, out, *, res=None, out2=None, act=ops.ACT_NONE, ld_out=None, name="linear", **kw):
         """out[M, n] = act(a[M, k] @ w[n, k]^T + bias (+ res)); ``ld_out`` > n writes into a column slice of a wider buffer"""
         n, k = w.shape
-        self._gemm(a, w, n, k, bias=bias, res=res, ld_res=n, out=out, ld_out=ld_out or n, out2=out2, ld_out2=n, act=act, name=name, **kw)
+        ld2 = out2.stride(0) if (out2 is not None and out2.dim() == 2) else n
+        self._gemm(a, w, n, k, bias=bias, res=res, ld_res=n, out=out, ld_out=ld_out or n, out2=out2, ld_out2=ld2, act=act, name=name, **kw)
 
     def _ln(self, x, gb, y, **kw):
         self.calls.append(ops.layernorm(x, gb[0], gb[1], y, **kw))
@@ -443,10 +483,14 @@ class DistEngine:
                    taps=[((k - half) * P, 0, 0) for k in range(a.t_kernel)], b_tap_stride=Ch * Ct, ldb=Ct,
                    groups=b, rows_per_group=T * P, bias=d["tn_b1"], out=self.y1, ld_out=Ch, act=ops.ACT_QUICKGELU,
                    name="dist.tn.conv_t")
-        self._gemm(self.y1, d["tn_w2"], Ct, Ch, a_dim=(Ch, g, g, b * T), a_stride=(1, Ch, g * Ch, P * Ch), img_w=g,
-                   taps=[(j - 1, ii - 1, 0) for ii in range(3) for j in range(3)], b_tap_stride=Ct * Ch, ldb=Ch,
-                   groups=b * T, rows_per_group=P, bias=d["tn_b2"], res=self.xT, ld_res=Ct, res_gstride=P,
-                   out=self.xT, ld_out=Ct, out2=self.xT_a, ld_out2=Ct, act=ops.ACT_QUICKGELU, name="dist.tn.conv_s")
+        conv_s = dict(a_dim=(Ch, g, g, b * T), a_stride=(1, Ch, g * Ch, P * Ch), img_w=g,
+                      taps=[(j - 1, ii - 1, 0) for ii in range(3) for j in range(3)], b_tap_stride=Ct * Ch, ldb=Ch,
+                      groups=b * T, rows_per_group=P, bias=d["tn_b2"], res=self.xT, ld_res=Ct, res_gstride=P,
+                      out=self.xT, ld_out=Ct, act=ops.ACT_QUICKGELU, name="dist.tn.conv_s")
+        if self.kcat:
+            self._plan_dist_layer_kcat(i, conv_s)
+            return
+        self._gemm(self.y1, d["tn_w2"], Ct, Ch, out2=self.xT_a, ld_out2=Ct, **conv_s)
 
         # ---- input linear + previous integration output (dist.py:229) ----
         self._lin(self.taps[a.selected_layers[i] % 2], d["in_w"], d["in_b"], self.mid, res=self.res if i > 0 else None, out2=self.mid_a,
@@ -492,6 +536,40 @@ class DistEngine:
                    groups=b, rows_per_group=t * N, bias=d["tf2_b"], out=self.int_h[:, Ih:], ld_out=wide, act=ops.ACT_QUICKGELU,
                    name="dist.int.t_conv")
         self._lin(self.int_h, d["prj_w"], d["prj_b"], self.res, name="dist.int.proj")
+
+    def _plan_dist_layer_kcat(self, i, conv_s):
+        """DiST layer i behind TemporalNet's first convolution, on the K-concatenated operand buffer (bf16 path):
+        columns [tap D | alpha temporal rows | one-hot(ti) | bf16 upd Ci] of the tap buffer of ViT block sel[i]."""
+        a, b, w = self.arch, self.batch, self.w
+        d = w.dist[i]
+        t, T, N, P = a.sparse_frames, a.frames, a.tokens, a.patches
+        F, Ci, Ct, al, Cm, Ih, D = b * t, a.integration_dim, a.temporal_dim, a.alpha, a.integration_temporal_hidden, a.integration_hidden, a.width
+        Mv = F * N
+        half = a.t_kernel // 2
+        buf, tw = self.tapw[a.selected_layers[i] % 2], self.tw
+        upd_a = buf[:, self.tw_u:]
+        # TemporalNet's (1,3,3) convolution drops the bf16 copy of dense frame alpha*ti + k next to token row 1 + r of sparse frame ti
+        self._gemm(self.y1, d["tn_w2"], Ct, a.temporal_hidden, out2=buf[:, D:], ld_out2=tw, out2_gdiv=al, out2_cstep=Ct, out2_gstride=N, out2_roff=1,
+                   **conv_s)
+        # input_linear + temporal->integration + cls token + previous integration output: upd in ONE pass (dist.py:229,80-86,232)
+        self._gemm(buf, d["cat_w"], Ci, self.tw_u, bias=d["cat_b"], res=self.res if i > 0 else None, ld_res=Ci, out=self.mid, ld_out=Ci,
+                   out2=upd_a, ld_out2=tw, name="dist.input_linear")
+        # integration -> temporal on the pre-fusion stream mid = upd - t2i(xT) (dist.py:99-105,231); dead in the last layer
+        if i < len(a.selected_layers) - 1:
+            k2 = self.tw_u + Ci - D
+            self._gemm(buf[:, D:], d["i2t_cat_w"], Ct, k2, a_dim=(k2, N, F, 1), a_stride=(1, tw, N * tw, Mv * tw), taps=[(1, 0, 0)],
+                       groups=F, rows_per_group=P, ldb=k2, bias=d["i2t_cat_b"], res=self.xT, ld_res=Ct, res_gstride=al * P,
+                       res_rep_stride=P, out=self.xT, ld_out=Ct, out_gstride=al * P, out_rep=al, out_rep_stride=P, name="dist.i2t")
+        # IntegrationNetwork (dist.py:16-45), both LayerNorms folded
+        wide = 2 * Cm + Ih
+        self.calls.append(ops.row_stats(upd_a[:, :Ci], self.int_st, name="dist.int.stats"))
+        self._gemm(upd_a[:, :Ci], d["int_wf"], Cm + Ih, Ci, bias=d["int_bf"], out=self.int_w, ld_out=wide, act=ops.ACT_QUICKGELU, act_from=Cm,
+                   ln_stats=self.int_st, ln_wsum=d["int_ws"], name="dist.int.fc")
+        self._gemm(self.int_w, d["tf2_w"], Cm, Cm, a_dim=(Cm, t * N, b, 1), a_stride=(1, wide, t * N * wide, Mv * wide),
+                   taps=[((k - half) * N, 0, 0) for k in range(a.t_kernel)], b_tap_stride=Cm * Cm, ldb=Cm,
+                   groups=b, rows_per_group=t * N, bias=d["tf2_b"], out=self.int_w[:, Cm + Ih:], ld_out=wide, act=ops.ACT_QUICKGELU,
+                   name="dist.int.t_conv")
+        self._lin(self.int_w[:, Cm:], d["prj_w"], d["prj_b"], self.res, name="dist.int.proj")
 
     def _plan_head(self):
         a, b, w = self.arch, self.batch, self.w

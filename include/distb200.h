@@ -117,7 +117,16 @@ typedef struct distb200_gemm_desc {
     /* The activation applies to the output columns n >= act_from only (0 = every column): lets one GEMM produce an activated and
      * a linear block side by side (IntegrationNetwork: temporal_ffn.c_fc1 | QuickGELU(ffn.c_fc), dist.py:40-45). */
     int32_t act_from;
+    /* Independent placement of out2 (0 = the rows of `out`): with out2_gdiv = g > 0 the copy of output row (gi, r) goes to row
+     * (gi / g) * out2_gstride + out2_roff + r, column offset (gi % g) * out2_cstep.  Lets the (1,3,3) convolution of
+     * TemporalNet drop the bf16 copy of frame alpha*ti + k next to token row 1 + r of sparse frame ti - the K-concatenated
+     * operand [tap | temporal rows | one-hot] from which input_linear, the temporal->integration convolution and the cls
+     * token (dist.py:229,80-86) come out of ONE GEMM.  Needs out_rep == 1. */
+    int32_t out2_gdiv;
+    int32_t out2_cstep;
     int32_t reserved0;
+    int64_t out2_gstride;
+    int64_t out2_roff;
 } distb200_gemm_desc;
 
 int distb200_gemm(const distb200_gemm_desc* desc, void* stream);
