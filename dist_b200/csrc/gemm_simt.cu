@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(NT) gemm_simt_kernel(const SimtArgs args) {
                 if (d.ln_stats) v = d.ln_stats[2 * orow + 1] * (v - d.ln_stats[2 * orow] * d.ln_wsum[n]);      // folded LayerNorm
                 if (d.bias) v += d.bias[n];
                 if (d.res) v += d.res[rsrc * d.ld_res + n];
-                if (d.act == DISTB200_ACT_QUICKGELU && n >= d.act_from) v = quick_gelu(v);
+                if (d.act == DISTB200_ACT_QUICKGELU && n >= d.act_from && (d.act_to == 0 || n < d.act_to)) v = quick_gelu(v);
                 if (d.out) {
                     if (d.out_dtype == DISTB200_F32) reinterpret_cast<float*>(d.out)[dst * d.ld_out + n] = v;
                     else reinterpret_cast<bf16*>(d.out)[dst * d.ld_out + n] = __float2bfloat16_rn(v);

@@ -164,7 +164,7 @@ struct Epi {
             o2 = reinterpret_cast<char*>(d.out2) + ((dst2_row0 + sub) * d.ld_out2 + n + col2) * es;
             s2 = 4 * d.ld_out2 * es;
         }
-        const bool act_on = ACT != 0 && n >= d.act_from;          // the activation may cover a column suffix only
+        const bool act_on = ACT != 0 && n >= d.act_from && (d.act_to == 0 || n < d.act_to);      // the activation may cover a column range only
         const float4* st4 = reinterpret_cast<const float4*>(stage);
         float4 vv[8];                      // all shared-memory reads first: their latency overlaps instead of serialising
 #pragma unroll
@@ -603,7 +603,8 @@ int gemm_tcgen05_launch(const distb200_gemm_desc& d, cudaStream_t stream) {
 
     DISTB200_REQUIRE(d.out2_gdiv >= 0 && (d.out2_gdiv == 0 || (d.out2 && d.out_rep == 1 && d.out2_cstep % 8 == 0 && d.groups < (1ll << 31))),
                     "gemm(tcgen05): out2_gdiv needs out2, out_rep == 1 and out2_cstep %% 8 == 0");
-    DISTB200_REQUIRE(d.act_from >= 0 && d.act_from % 4 == 0, "gemm(tcgen05): act_from=%d must be a non-negative multiple of 4", d.act_from);
+    DISTB200_REQUIRE(d.act_from >= 0 && d.act_from % 4 == 0 && d.act_to >= 0 && d.act_to % 4 == 0,
+                    "gemm(tcgen05): act_from=%d / act_to=%d must be non-negative multiples of 4", d.act_from, d.act_to);
     if (d.stat_partials) {
         DISTB200_REQUIRE(d.out && d.out_dtype == DISTB200_F32 && d.out2 && d.out2_dtype == DISTB200_BF16 && d.res && d.act == DISTB200_ACT_NONE &&
                         d.out_rep == 1 && !d.ln_stats, "gemm(tcgen05): stat_partials needs fp32 out + bf16 out2 + res, no activation, out_rep 1");

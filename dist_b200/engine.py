@@ -28,11 +28,16 @@ def _pad8(n):
     return (n + 7) // 8 * 8
 
 
-def _onehot_width(arch):
-    """Columns reserved for one-hot(ti) in the K-concatenated operand: at least t, and such that the bf16 `upd` block behind
-    it starts on a 128-byte boundary (64 elements)."""
-    base = arch.width + arch.alpha * arch.temporal_dim
-    return (base + arch.sparse_frames + 63) // 64 * 64 - base
+def kcat_layout(arch):
+    """Column layout of the K-concatenated DiST operand buffer (bf16 path), every block on a 128-byte boundary:
+    [tap D | hidden activations of the PREVIOUS IntegrationNetwork (ffn Ih | c_fc1 Cm | temporal Cm) | alpha temporal rows |
+     one-hot(ti) | bf16 upd Ci]."""
+    r64 = lambda n: (n + 63) // 64 * 64
+    c_h = r64(arch.width)
+    c_x = r64(c_h + arch.integration_hidden + 2 * arch.integration_temporal_hidden)
+    c_oh = r64(c_x + arch.alpha * arch.temporal_dim)
+    c_u = r64(c_oh + arch.sparse_frames)
+    return dict(c_h=c_h, c_x=c_x, c_oh=c_oh, c_u=c_u, tw=r64(c_u + arch.integration_dim))
 
 
 def plan_branches(names, sel):
@@ -156,35 +161,53 @@ class PackedWeights:
                 tf2_w=op(wk), tf2_b=f32(sd[it + "temporal_ffn.c_fc2.bias"]),
             ))
             # IntegrationNetwork with both LayerNorms folded (bf16 path): ONE GEMM on the raw rows of `upd` produces
-            # [temporal_ffn.c_fc1(LN_t x) | ffn.c_fc(LN x)] - operand rows [W_tf1 * gamma_t ; W_fc * gamma], their row sums
-            # (of the rounded operand) and the biases W beta + b; QuickGELU covers the ffn columns only (dist.py:40-45)
+            # [QuickGELU(ffn.c_fc(LN x)) | temporal_ffn.c_fc1(LN_t x)] - operand rows [W_fc * gamma ; W_tf1 * gamma_t], their row sums
+            # (of the rounded operand) and the biases W beta + b; the activation covers the ffn columns only (dist.py:40-45)
             wt = sd[it + "temporal_ffn.c_fc1.weight"].detach().double()[:, :, 0, 0, 0]
             wf = sd[it + "ffn.c_fc.weight"].detach().double()
             g1, b1 = sd[it + "ln.weight"].detach().double(), sd[it + "ln.bias"].detach().double()
             g2, b2 = sd[it + "ln_temporal.weight"].detach().double(), sd[it + "ln_temporal.bias"].detach().double()
-            cat = torch.cat([wt * g2[None, :], wf * g1[None, :]], dim=0).float().to(device=device).to(act_dtype).contiguous()
-            # K-concatenated operands (bf16 path, DistEngine.kcat): columns [tap D | alpha temporal rows | one-hot(ti) | upd Ci]
-            #   mid/upd = [tap | xT pair | e_ti] . [W_in | W_t2i,0 .. W_t2i,alpha-1 | cls_ti - b_t2i]^T + (b_in + b_t2i)   (dist.py:229,80-86,232)
-            #   i2t     = [xT pair | e_ti | upd] . [-W_i2t W_t2i | 0 | W_i2t]^T + (b_i2t - W_i2t b_t2i)   on the patch rows,
-            #             i.e. linear_fuse(mid) with mid = upd - t2i(xT) (dist.py:99-105,231 reads the PRE-fusion mid)
-            oh = _onehot_width(a)
-            w_in = sd["dist_net.input_linears.%d.weight" % i].detach().double().cpu()
-            wt2 = sd[t2i + "linear_fuse.weight"].detach().double().cpu()[:, :, :, 0, 0].permute(2, 0, 1)          # [alpha, Ci, Ct]
-            b_t2 = sd[t2i + "linear_fuse.bias"].detach().double().cpu()
-            cls = sd[t2i + "cls_token"].detach().double().cpu().reshape(a.sparse_frames, Ci)
+            # K-concatenated operands (bf16 path, DistEngine.kcat; column layout = kcat_layout):
+            #   upd_i = [tap | h_{i-1} | xT pair | e_ti] . [W_in | W_proj,i-1 | W_t2i,0..alpha-1 | cls_ti - b_t2i]^T + (b_in + b_t2i + b_proj,i-1)
+            #           = input_linear(tap) + res_{i-1} + t2i(xT) + cls token (dist.py:229,80-86,232) with the previous
+            #           IntegrationNetwork's output projection res_{i-1} = h_{i-1} W_proj^T + b (dist.py:45) riding in the same reduction
+            #   i2t   = [xT pair | e_ti | upd] . [-W_i2t W_t2i | 0 | W_i2t]^T + (b_i2t - W_i2t b_t2i)   on the patch rows,
+            #           i.e. linear_fuse(mid) with mid = upd - t2i(xT) (dist.py:99-105,231 reads the PRE-fusion mid)
+            KL = kcat_layout(a)
+            Ih, Cm = a.integration_hidden, a.integration_temporal_hidden
+            cpu64 = lambda x: x.detach().double().cpu()
+            w_in = cpu64(sd["dist_net.input_linears.%d.weight" % i])
+            wt2 = cpu64(sd[t2i + "linear_fuse.weight"])[:, :, :, 0, 0].permute(2, 0, 1)                     # [alpha, Ci, Ct]
+            b_t2 = cpu64(sd[t2i + "linear_fuse.bias"])
+            cls = cpu64(sd[t2i + "cls_token"]).reshape(a.sparse_frames, Ci)
             w_t2_flat = torch.cat([wt2[k] for k in range(a.alpha)], dim=1)                                   # [Ci, alpha*Ct]
-            onehot = torch.zeros(Ci, oh, dtype=torch.float64)
-            onehot[:, :a.sparse_frames] = (cls - b_t2[None, :]).t()
-            w_i2 = sd[i2t + "linear_fuse.weight"].detach().double().cpu()                                          # [Ct, Ci]
-            i2_cat = torch.cat([-(w_i2 @ w_t2_flat), torch.zeros(Ct, oh, dtype=torch.float64), w_i2], dim=1)
+            cat_w = torch.zeros(Ci, KL["c_u"], dtype=torch.float64)
+            cat_w[:, :D] = w_in
+            cat_b = cpu64(sd["dist_net.input_linears.%d.bias" % i]) + b_t2
+            if i > 0:
+                pit = "dist_net.integration_nets.%d." % (i - 1)
+                cat_w[:, KL["c_h"]:KL["c_h"] + Ih] = cpu64(sd[pit + "ffn.c_proj.weight"])
+                cat_w[:, KL["c_h"] + Ih + Cm:KL["c_h"] + Ih + 2 * Cm] = cpu64(sd[pit + "temporal_ffn.c_proj.weight"])[:, :, 0, 0, 0]
+                cat_b = cat_b + cpu64(sd[pit + "ffn.c_proj.bias"]) + cpu64(sd[pit + "temporal_ffn.c_proj.bias"])
+            cat_w[:, KL["c_x"]:KL["c_x"] + a.alpha * Ct] = w_t2_flat
+            cat_w[:, KL["c_oh"]:KL["c_oh"] + a.sparse_frames] = (cls - b_t2[None, :]).t()
+            w_i2 = cpu64(sd[i2t + "linear_fuse.weight"])                                                     # [Ct, Ci]
+            i2_cat = torch.zeros(Ct, KL["c_u"] + Ci - KL["c_x"], dtype=torch.float64)
+            i2_cat[:, :a.alpha * Ct] = -(w_i2 @ w_t2_flat)
+            i2_cat[:, KL["c_u"] - KL["c_x"]:] = w_i2
+            # IntegrationNetwork hidden block [QuickGELU(ffn.c_fc) Ih | temporal c_fc1 Cm | temporal hidden Cm]: folded c_fc / c_fc1 rows
+            # in that order, and the last layer's output projection over the same block (zero weights on the c_fc1 columns)
+            cat2 = torch.cat([wf * g1[None, :], wt * g2[None, :]], dim=0).float().to(device=device).to(act_dtype).contiguous()
+            prj = torch.zeros(Ci, Ih + 2 * Cm, dtype=torch.float64)
+            prj[:, :Ih] = cpu64(sd[it + "ffn.c_proj.weight"])
+            prj[:, Ih + Cm:] = cpu64(sd[it + "temporal_ffn.c_proj.weight"])[:, :, 0, 0, 0]
             self.dist[-1].update(
-                cat_w=op(torch.cat([w_in, w_t2_flat, onehot], dim=1).float()),
-                cat_b=f32(sd["dist_net.input_linears.%d.bias" % i].detach().double().cpu() + b_t2),
-                i2t_cat_w=op(i2_cat.float()), i2t_cat_b=f32(sd[i2t + "linear_fuse.bias"].detach().double().cpu() - w_i2 @ b_t2))
-            self.dist[-1].update(
-                int_wf=cat, int_ws=cat.float().sum(dim=1).contiguous(),
-                int_bf=f32(torch.cat([wt @ b2 + sd[it + "temporal_ffn.c_fc1.bias"].detach().double(),
-                                      wf @ b1 + sd[it + "ffn.c_fc.bias"].detach().double()])))
+                cat_w=op(cat_w.float()), cat_b=f32(cat_b), i2t_cat_w=op(i2_cat.float()),
+                i2t_cat_b=f32(cpu64(sd[i2t + "linear_fuse.bias"]) - w_i2 @ b_t2),
+                int_wf2=cat2, int_ws2=cat2.float().sum(dim=1).contiguous(),
+                int_bf2=f32(torch.cat([wf @ b1 + sd[it + "ffn.c_fc.bias"].detach().double(),
+                                       wt @ b2 + sd[it + "temporal_ffn.c_fc1.bias"].detach().double()])),
+                prj_w_h=op(prj.float()))
         self.ada = []
         for j in range(a.ada_layers):
             pre = "dist_net.adapooling_nets.%d." % j
@@ -268,19 +291,16 @@ class DistEngine:
         # bf16 copies of the ViT block outputs (the taps; with the folded LayerNorm also the next block's GEMM operand).  Two
         # buffers, alternating by layer, so that the DiST layer reading tap l may still run while ViT block l+1 writes its own.
         self.ln_fold = self.precision == "bf16" and os.environ.get("DISTB200_LN_FOLD", "1") != "0"
-        self.int_fold = self.ln_fold and os.environ.get("DISTB200_INT_FOLD", "1") != "0"
         # K-concatenated DiST operands (see PackedWeights): the tap buffers grow the columns [alpha temporal rows | one-hot(ti) |
         # bf16 upd]; input_linear + the temporal->integration convolution + the cls token become ONE GEMM, `mid` is written once
-        self.kcat = self.int_fold and os.environ.get("DISTB200_KCAT", "1") != "0"
+        self.kcat = self.ln_fold and os.environ.get("DISTB200_KCAT", "1") != "0"
         if self.kcat:
-            oh = _onehot_width(a)
-            self.tw_oh = D + a.alpha * Ct
-            self.tw_u = self.tw_oh + oh
-            self.tw = (self.tw_u + Ci + 63) // 64 * 64          # row pitch: whole 128-byte lines
+            self.kl = kcat_layout(a)
+            self.tw = self.kl["tw"]
             self.tapw = [z(Mv, self.tw), z(Mv, self.tw)]
             frames = torch.arange(F, device=dev)
             for buf in self.tapw:                      # static one-hot(ti) on the class-token row of every frame
-                buf[frames * N, self.tw_oh + frames % a.sparse_frames] = 1.0
+                buf[frames * N, self.kl["c_oh"] + frames % a.sparse_frames] = 1.0
             self.taps = [buf[:, :D] for buf in self.tapw]
         else:
             self.taps = [z(Mv, D), z(Mv, D)] if self.precision == "bf16" else [self.h, self.h]
@@ -310,12 +330,9 @@ class DistEngine:
         self.int_a1 = z(Mv, Ci)
         self.int_a2 = z(Mv, Ci)
         self.int_h = z(Mv, a.integration_hidden + a.integration_temporal_hidden)     # [ffn hidden | temporal hidden]
-        # folded IntegrationNetwork (bf16 path): bf16 copy of `upd`, its row statistics, and one wide activation buffer
-        # [temporal c_fc1 output | ffn hidden | temporal hidden] so that every consumer reads a column slice of it
-        if self.int_fold:
-            self.upd_a = None if self.kcat else z(Mv, Ci)
-            self.int_st = z(Mv, 2, dtype=f32)
-            self.int_w = z(Mv, 2 * a.integration_temporal_hidden + a.integration_hidden)
+        if self.kcat:
+            self.int_st = z(Mv, 2, dtype=f32)                                           # row statistics of upd (both LayerNorms folded)
+            self.int_w = z(Mv, 2 * a.integration_temporal_hidden + a.integration_hidden)     # the LAST layer's hidden block
         self.tf1 = z(Mv, a.integration_temporal_hidden)
         self.kv_s = z(Mv, 2 * Ci)
         self.sp = z(F, Ci, dtype=f32)
@@ -500,10 +517,8 @@ class DistEngine:
         self._gemm(self.xT_a, d["t2i_w"], Ci, Ct, a_dim=(Ct, P, al, F), a_stride=(1, Ct, P * Ct, al * P * Ct), group_dim=3,
                    taps=[(0, k, 0) for k in range(al)], b_tap_stride=Ci * Ct, ldb=Ct, groups=F, rows_per_group=P,
                    bias=d["t2i_b"], res=self.mid, ld_res=Ci, res_gstride=N, res_roff=1,
-                   out=self.mid, ld_out=Ci, out_gstride=N, out_roff=1, out2=self.upd_a if self.int_fold else None, ld_out2=Ci,
-                   name="dist.t2i")
-        add(ops.rows_bcast(self.mid, N * Ci, F, Ci, d["t2i_cls"], t, True, dst2=self.upd_a if self.int_fold else None, row_stride2=N * Ci,
-                           name="dist.t2i.cls"))
+                   out=self.mid, ld_out=Ci, out_gstride=N, out_roff=1, name="dist.t2i")
+        add(ops.rows_bcast(self.mid, N * Ci, F, Ci, d["t2i_cls"], t, True, name="dist.t2i.cls"))
 
         # ---- integration -> temporal (dist.py:90-105,231): patch tokens only, nearest upsample = row replication
         # (the fused temporal stream of the LAST layer is read by nothing, dist.py:231-235: its branch is skipped)
@@ -513,18 +528,6 @@ class DistEngine:
                        res_rep_stride=P, out=self.xT, ld_out=Ct, out_gstride=al * P, out_rep=al, out_rep_stride=P, name="dist.i2t")
 
         # ---- IntegrationNetwork (dist.py:16-45) on upd = mid ----
-        if self.int_fold:
-            # both LayerNorms folded into one GEMM over the bf16 copy of upd (written by the t2i epilogue and the cls-token kernel)
-            Ih, wide = a.integration_hidden, 2 * Cm + a.integration_hidden
-            add(ops.row_stats(self.upd_a, self.int_st, name="dist.int.stats"))
-            self._gemm(self.upd_a, d["int_wf"], Cm + Ih, Ci, bias=d["int_bf"], out=self.int_w, ld_out=wide, act=ops.ACT_QUICKGELU, act_from=Cm,
-                       ln_stats=self.int_st, ln_wsum=d["int_ws"], name="dist.int.fc")
-            self._gemm(self.int_w, d["tf2_w"], Cm, Cm, a_dim=(Cm, t * N, b, 1), a_stride=(1, wide, t * N * wide, Mv * wide),
-                       taps=[((k - half) * N, 0, 0) for k in range(a.t_kernel)], b_tap_stride=Cm * Cm, ldb=Cm,
-                       groups=b, rows_per_group=t * N, bias=d["tf2_b"], out=self.int_w[:, Cm + Ih:], ld_out=wide, act=ops.ACT_QUICKGELU,
-                       name="dist.int.t_conv")
-            self._lin(self.int_w[:, Cm:], d["prj_w"], d["prj_b"], self.res, name="dist.int.proj")
-            return
         add(ops.layernorm(self.mid, d["ln"][0], d["ln"][1], self.int_a1, g2=d["ln_t"][0], b2=d["ln_t"][1], y2=self.int_a2,
                           name="dist.int.ln"))
         Ih = a.integration_hidden
@@ -538,38 +541,42 @@ class DistEngine:
         self._lin(self.int_h, d["prj_w"], d["prj_b"], self.res, name="dist.int.proj")
 
     def _plan_dist_layer_kcat(self, i, conv_s):
-        """DiST layer i behind TemporalNet's first convolution, on the K-concatenated operand buffer (bf16 path):
-        columns [tap D | alpha temporal rows | one-hot(ti) | bf16 upd Ci] of the tap buffer of ViT block sel[i]."""
+        """DiST layer i behind TemporalNet's first convolution, on the K-concatenated operand buffers (bf16 path, kcat_layout)."""
         a, b, w = self.arch, self.batch, self.w
         d = w.dist[i]
+        sel = list(a.selected_layers)
         t, T, N, P = a.sparse_frames, a.frames, a.tokens, a.patches
-        F, Ci, Ct, al, Cm, Ih, D = b * t, a.integration_dim, a.temporal_dim, a.alpha, a.integration_temporal_hidden, a.integration_hidden, a.width
+        F, Ci, Ct, al, Cm, Ih = b * t, a.integration_dim, a.temporal_dim, a.alpha, a.integration_temporal_hidden, a.integration_hidden
         Mv = F * N
         half = a.t_kernel // 2
-        buf, tw = self.tapw[a.selected_layers[i] % 2], self.tw
-        upd_a = buf[:, self.tw_u:]
+        last = i == len(sel) - 1
+        L, tw = self.kl, self.tw
+        buf = self.tapw[sel[i] % 2]
+        upd_a = buf[:, L["c_u"]:L["c_u"] + Ci]
         # TemporalNet's (1,3,3) convolution drops the bf16 copy of dense frame alpha*ti + k next to token row 1 + r of sparse frame ti
-        self._gemm(self.y1, d["tn_w2"], Ct, a.temporal_hidden, out2=buf[:, D:], ld_out2=tw, out2_gdiv=al, out2_cstep=Ct, out2_gstride=N, out2_roff=1,
-                   **conv_s)
-        # input_linear + temporal->integration + cls token + previous integration output: upd in ONE pass (dist.py:229,80-86,232)
-        self._gemm(buf, d["cat_w"], Ci, self.tw_u, bias=d["cat_b"], res=self.res if i > 0 else None, ld_res=Ci, out=self.mid, ld_out=Ci,
-                   out2=upd_a, ld_out2=tw, name="dist.input_linear")
+        self._gemm(self.y1, d["tn_w2"], Ct, a.temporal_hidden, out2=buf[:, L["c_x"]:], ld_out2=tw, out2_gdiv=al, out2_cstep=Ct, out2_gstride=N,
+                   out2_roff=1, **conv_s)
+        # upd in ONE pass: input_linear + previous IntegrationNetwork's output projection + temporal->integration + cls token
+        self._gemm(buf, d["cat_w"], Ci, L["c_u"], bias=d["cat_b"], out=self.mid, ld_out=Ci, out2=upd_a, ld_out2=tw, name="dist.input_linear")
         # integration -> temporal on the pre-fusion stream mid = upd - t2i(xT) (dist.py:99-105,231); dead in the last layer
-        if i < len(a.selected_layers) - 1:
-            k2 = self.tw_u + Ci - D
-            self._gemm(buf[:, D:], d["i2t_cat_w"], Ct, k2, a_dim=(k2, N, F, 1), a_stride=(1, tw, N * tw, Mv * tw), taps=[(1, 0, 0)],
+        if not last:
+            k2 = L["c_u"] + Ci - L["c_x"]
+            self._gemm(buf[:, L["c_x"]:], d["i2t_cat_w"], Ct, k2, a_dim=(k2, N, F, 1), a_stride=(1, tw, N * tw, Mv * tw), taps=[(1, 0, 0)],
                        groups=F, rows_per_group=P, ldb=k2, bias=d["i2t_cat_b"], res=self.xT, ld_res=Ct, res_gstride=al * P,
                        res_rep_stride=P, out=self.xT, ld_out=Ct, out_gstride=al * P, out_rep=al, out_rep_stride=P, name="dist.i2t")
-        # IntegrationNetwork (dist.py:16-45), both LayerNorms folded
-        wide = 2 * Cm + Ih
-        self.calls.append(ops.row_stats(upd_a[:, :Ci], self.int_st, name="dist.int.stats"))
-        self._gemm(upd_a[:, :Ci], d["int_wf"], Cm + Ih, Ci, bias=d["int_bf"], out=self.int_w, ld_out=wide, act=ops.ACT_QUICKGELU, act_from=Cm,
-                   ln_stats=self.int_st, ln_wsum=d["int_ws"], name="dist.int.fc")
-        self._gemm(self.int_w, d["tf2_w"], Cm, Cm, a_dim=(Cm, t * N, b, 1), a_stride=(1, wide, t * N * wide, Mv * wide),
+        # IntegrationNetwork (dist.py:16-45), both LayerNorms folded; its hidden block lands next to the NEXT layer's tap, where that
+        # layer's first GEMM applies the output projection (the last layer projects here: the ada-pooling head reads `res`)
+        hbuf = self.int_w if last else self.tapw[sel[i + 1] % 2][:, L["c_h"]:]
+        hp = hbuf.stride(0)
+        self.calls.append(ops.row_stats(upd_a, self.int_st, name="dist.int.stats"))
+        self._gemm(upd_a, d["int_wf2"], Ih + Cm, Ci, bias=d["int_bf2"], out=hbuf, ld_out=hp, act=ops.ACT_QUICKGELU, act_to=Ih,
+                   ln_stats=self.int_st, ln_wsum=d["int_ws2"], name="dist.int.fc")
+        self._gemm(hbuf[:, Ih:], d["tf2_w"], Cm, Cm, a_dim=(Cm, t * N, b, 1), a_stride=(1, hp, t * N * hp, Mv * hp),
                    taps=[((k - half) * N, 0, 0) for k in range(a.t_kernel)], b_tap_stride=Cm * Cm, ldb=Cm,
-                   groups=b, rows_per_group=t * N, bias=d["tf2_b"], out=self.int_w[:, Cm + Ih:], ld_out=wide, act=ops.ACT_QUICKGELU,
+                   groups=b, rows_per_group=t * N, bias=d["tf2_b"], out=hbuf[:, Ih + Cm:], ld_out=hp, act=ops.ACT_QUICKGELU,
                    name="dist.int.t_conv")
-        self._lin(self.int_w[:, Cm:], d["prj_w"], d["prj_b"], self.res, name="dist.int.proj")
+        if last:
+            self._lin(self.int_w, d["prj_w_h"], d["prj_b"], self.res, name="dist.int.proj")
 
     def _plan_head(self):
         a, b, w = self.arch, self.batch, self.w

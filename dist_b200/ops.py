@@ -40,7 +40,7 @@ class GemmDesc(C.Structure):
         ("out2", C.c_void_p), ("out2_dtype", C.c_int32), ("act", C.c_int32),
         ("ld_out2", C.c_int64), ("block_n", C.c_int32), ("group_dim", C.c_int32),
         ("ln_stats", C.c_void_p), ("ln_wsum", C.c_void_p), ("stat_partials", C.c_void_p),
-        ("act_from", C.c_int32), ("out2_gdiv", C.c_int32), ("out2_cstep", C.c_int32), ("reserved0", C.c_int32),
+        ("act_from", C.c_int32), ("out2_gdiv", C.c_int32), ("out2_cstep", C.c_int32), ("act_to", C.c_int32),
         ("out2_gstride", C.c_int64), ("out2_roff", C.c_int64),
     ]
 
@@ -171,7 +171,7 @@ class Call:
 def gemm(a, b, n, k, *, a_dim=None, a_stride=None, taps=((0, 0, 0),), b_tap_stride=0, ldb=None, img_w=0,
          groups=1, rows_per_group=None, group_dim=2, bias=None, res=None, ld_res=0, res_gstride=0, res_roff=0,
          res_rep_stride=0, out=None, ld_out=0, out_gstride=None, out_roff=0, out_rep=1, out_rep_stride=0,
-         out2=None, ld_out2=0, act=ACT_NONE, impl=IMPL_AUTO, block_n=0, ln_stats=None, ln_wsum=None, stat_partials=None, act_from=0, out2_gdiv=0, out2_cstep=0, out2_gstride=0, out2_roff=0, name="gemm"):
+         out2=None, ld_out2=0, act=ACT_NONE, impl=IMPL_AUTO, block_n=0, ln_stats=None, ln_wsum=None, stat_partials=None, act_from=0, act_to=0, out2_gdiv=0, out2_cstep=0, out2_gstride=0, out2_roff=0, name="gemm"):
     """Prepare one ``distb200_gemm`` (see the header for the exact definition).
 
     Defaults describe a plain ``out[M, n] = a[M, k] @ b[n, k]^T``: ``a`` is a 2-D row-major tensor,
@@ -216,7 +216,7 @@ def gemm(a, b, n, k, *, a_dim=None, a_stride=None, taps=((0, 0, 0),), b_tap_stri
     d.ln_stats, d.ln_wsum = _ptr(ln_stats), _ptr(ln_wsum)
     assert (ln_stats is None) == (ln_wsum is None)
     d.stat_partials = _ptr(stat_partials)
-    d.act_from = int(act_from)
+    d.act_from, d.act_to = int(act_from), int(act_to)
     d.out2_gdiv, d.out2_cstep, d.out2_gstride, d.out2_roff = int(out2_gdiv), int(out2_cstep), int(out2_gstride), int(out2_roff)
     if stat_partials is not None:
         assert stat_partials.dtype == torch.float32 and stat_partials.numel() >= int(groups) * int(rows_per_group) * STAT_SLOTS * 2

@@ -114,8 +114,8 @@ typedef struct distb200_gemm_desc {
      * distb200_row_stats_finalize reduces the slots to the (mean, rstd) pairs that ln_stats takes: the stand-alone pass over
      * the bf16 copy (distb200_row_stats) disappears.  Needs fp32 out + bf16 out2 + res, no activation, out_rep == 1, tcgen05. */
     float* stat_partials;
-    /* The activation applies to the output columns n >= act_from only (0 = every column): lets one GEMM produce an activated and
-     * a linear block side by side (IntegrationNetwork: temporal_ffn.c_fc1 | QuickGELU(ffn.c_fc), dist.py:40-45). */
+    /* The activation applies to the output columns act_from <= n < act_to only (act_to 0 = up to n): lets one GEMM produce an
+     * activated and a linear block side by side (IntegrationNetwork: QuickGELU(ffn.c_fc) | temporal_ffn.c_fc1, dist.py:40-45). */
     int32_t act_from;
     /* Independent placement of out2 (0 = the rows of `out`): with out2_gdiv = g > 0 the copy of output row (gi, r) goes to row
      * (gi / g) * out2_gstride + out2_roff + r, column offset (gi % g) * out2_cstep.  Lets the (1,3,3) convolution of
@@ -124,7 +124,7 @@ typedef struct distb200_gemm_desc {
      * token (dist.py:229,80-86) come out of ONE GEMM.  Needs out_rep == 1. */
     int32_t out2_gdiv;
     int32_t out2_cstep;
-    int32_t reserved0;
+    int32_t act_to;
     int64_t out2_gstride;
     int64_t out2_roff;
 } distb200_gemm_desc;

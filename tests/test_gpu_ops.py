@@ -337,8 +337,8 @@ def test_gemm_emits_row_statistics(M, N, K, impl):
 
 @pytest.mark.parametrize("impl", ["tcgen05", "simt"])
 def test_gemm_activation_on_a_column_suffix_and_bcast_copy(impl):
-    """distb200_gemm_desc.act_from: QuickGELU on the columns n >= act_from only (folded IntegrationNetwork: linear temporal
-    block | activated ffn block out of one GEMM); rows_bcast's optional bf16 copy of the rows it produced."""
+    """distb200_gemm_desc.act_from / act_to: QuickGELU on a column range only (folded IntegrationNetwork: activated ffn block |
+    linear temporal block out of one GEMM); rows_bcast's optional bf16 copy of the rows it produced."""
     ops = _ops()
     g = torch.Generator().manual_seed(5)
     M, N, K, cut = 333, 480, 384, 96
@@ -352,6 +352,12 @@ def test_gemm_activation_on_a_column_suffix_and_bcast_copy(impl):
     ref[:, cut:] = _qgelu(ref[:, cut:])
     assert rel_l2(wide[:, :cut], ref[:, :cut]) < 4e-3 and rel_l2(wide[:, cut:N], ref[:, cut:]) < 6e-3
     assert float(wide[:, N:].abs().max()) == 0.0
+    lo, hi = 64, 416                                                  # ... and on an inner column range
+    _run(ops.gemm(a, w, N, K, bias=bias, out=wide, ld_out=576, act=ops.ACT_QUICKGELU, act_from=lo, act_to=hi,
+                  impl=ops.IMPL_SIMT if impl == "simt" else ops.IMPL_AUTO))
+    ref = a.double() @ w.double().t() + bias.double()
+    ref[:, lo:hi] = _qgelu(ref[:, lo:hi])
+    assert rel_l2(wide[:, :lo], ref[:, :lo]) < 4e-3 and rel_l2(wide[:, lo:hi], ref[:, lo:hi]) < 6e-3 and rel_l2(wide[:, hi:N], ref[:, hi:]) < 4e-3
     dst = torch.randn(10, 5 * 16, generator=g).to(DEV)
     want = dst.clone()
     table = torch.randn(4, 16, generator=g).to(DEV)
@@ -359,3 +365,30 @@ def test_gemm_activation_on_a_column_suffix_and_bcast_copy(impl):
     _run(ops.rows_bcast(dst, 5 * 16, 10, 16, table, 4, True, dst2=copy, row_stride2=5 * 16))
     want[:, :16] += table[torch.arange(10) % 4]
     assert torch.equal(dst, want) and torch.equal(copy[:, :16], want[:, :16].to(torch.bfloat16)) and float(copy[:, 16:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("impl", ["tcgen05", "simt"])
+def test_gemm_places_out2_independently(impl):
+    """distb200_gemm_desc.out2_gdiv / out2_cstep / out2_gstride / out2_roff: the bf16 copy of output row (gi, r) lands at row
+    (gi / g) * gstride + roff + r, column offset (gi % g) * cstep of a wider buffer (TemporalNet's (1,3,3) convolution feeding
+    the K-concatenated operand), while `out` keeps its own rows."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(9)
+    groups, rpg, N, K, gdiv, gstride, roff, pitch, col0 = 6, 49, 96, 96, 2, 50, 1, 512, 128
+    a = (torch.randn(groups * rpg, K, generator=g) / K ** 0.5).to(torch.bfloat16).to(DEV)
+    w = torch.randn(N, K, generator=g).to(torch.bfloat16).to(DEV)
+    out = torch.zeros(groups * rpg, N, device=DEV)
+    wide = torch.zeros((groups // gdiv) * gstride, pitch, device=DEV, dtype=torch.bfloat16)
+    _run(ops.gemm(a, w, N, K, a_dim=(K, rpg, groups, 1), a_stride=(1, K, rpg * K, groups * rpg * K), groups=groups, rows_per_group=rpg,
+                  out=out, ld_out=N, out2=wide[:, col0:], ld_out2=pitch, out2_gdiv=gdiv, out2_cstep=N, out2_gstride=gstride, out2_roff=roff,
+                  impl=ops.IMPL_SIMT if impl == "simt" else ops.IMPL_AUTO))
+    ref = (a.double() @ w.double().t()).cpu()
+    assert rel_l2(out, ref) < 1e-5
+    want = torch.zeros_like(wide, dtype=torch.float64).cpu()
+    for gi in range(groups):
+        r0 = (gi // gdiv) * gstride + roff
+        c0 = col0 + (gi % gdiv) * N
+        want[r0:r0 + rpg, c0:c0 + N] = ref[gi * rpg:(gi + 1) * rpg]
+    got = wide.double().cpu()
+    assert torch.equal(got == 0, want == 0) or float((got - want).abs().max()) < 0.05      # untouched cells stay zero
+    assert rel_l2(got, want) < 4e-3
