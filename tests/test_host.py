@@ -211,3 +211,56 @@ def test_graph_branches_dependencies():
     assert deps[at("tail.proj_spatial_cls", 0)] == [at("dist.cls_mean", 0)]
     for k, ds in deps.items():                                    # every edge points backwards in plan order and crosses branches
         assert all(d < k and branch[d] != branch[k] for d in ds)
+
+
+def test_kcat_layout_and_weight_algebra():
+    """The K-concatenated DiST operands (engine.kcat_layout / PackedWeights): in fp64 on the CPU, one product with the concatenated
+    weights equals input_linear + previous output projection + temporal->integration convolution + cls token
+    (dist.py:229,45,80-86,232), and the re-expressed integration->temporal product equals linear_fuse of the PRE-fusion stream
+    (dist.py:99-105,231)."""
+    from dist_b200.engine import PackedWeights, kcat_layout
+    from dist_b200.utils import synth
+    arch = tiny_arch(frames=6, alpha=3, resolution=96, selected_layers=[0, 1])
+    L = kcat_layout(arch)
+    D, Ci, Ct, al, t = arch.width, arch.integration_dim, arch.temporal_dim, arch.alpha, arch.sparse_frames
+    Ih, Cm = arch.integration_hidden, arch.integration_temporal_hidden
+    assert all(v % 64 == 0 for v in L.values())
+    assert L["c_h"] >= D and L["c_x"] >= L["c_h"] + Ih + 2 * Cm and L["c_oh"] >= L["c_x"] + al * Ct and L["c_u"] >= L["c_oh"] + t
+    assert L["tw"] >= L["c_u"] + Ci
+    big = DistArch()
+    LB = kcat_layout(big)
+    assert (LB["c_h"], LB["c_x"], LB["c_oh"], LB["c_u"], LB["tw"]) == (768, 1344, 1536, 1600, 1984)
+
+    sd = {k: v.double() for k, v in synth.synth_state_dict(arch, seed=3, init="scaled").items()}
+    w = PackedWeights(sd, arch, "cpu", torch.float64)
+    g = torch.Generator().manual_seed(0)
+    for i in (0, 1):
+        d = w.dist[i]
+        assert d["cat_w"].shape == (Ci, L["c_u"]) and d["i2t_cat_w"].shape == (Ct, L["c_u"] + Ci - L["c_x"])
+        ti = 1
+        tap = torch.randn(5, D, generator=g, dtype=torch.float64)
+        h_prev = torch.randn(5, Ih + 2 * Cm, generator=g, dtype=torch.float64)       # [ffn hidden | c_fc1 output | temporal hidden]
+        xt = torch.randn(5, al, Ct, generator=g, dtype=torch.float64)                # the alpha dense frames of sparse frame ti
+        rows = torch.zeros(5, L["c_u"], dtype=torch.float64)
+        rows[:, :D] = tap
+        rows[:, L["c_h"]:L["c_h"] + Ih + 2 * Cm] = h_prev
+        rows[1:, L["c_x"]:L["c_x"] + al * Ct] = xt[1:].reshape(4, -1)                # row 0 plays the class token: no temporal rows,
+        rows[0, L["c_oh"] + ti] = 1.0                                                 # a one-hot(ti) instead
+        upd = rows @ d["cat_w"].t() + d["cat_b"]
+        lin = lambda x, p: x @ sd[p + ".weight"].t() + sd[p + ".bias"]
+        want = lin(tap, "dist_net.input_linears.%d" % i)
+        if i > 0:
+            pit = "dist_net.integration_nets.%d." % (i - 1)
+            want = (want + h_prev[:, :Ih] @ sd[pit + "ffn.c_proj.weight"].t() + sd[pit + "ffn.c_proj.bias"]
+                    + h_prev[:, Ih + Cm:] @ sd[pit + "temporal_ffn.c_proj.weight"][:, :, 0, 0, 0].t() + sd[pit + "temporal_ffn.c_proj.bias"])
+        t2i = "dist_net.temporal2integration_nets.%d." % i
+        wt = sd[t2i + "linear_fuse.weight"][:, :, :, 0, 0]                            # [Ci, Ct, alpha]
+        v = torch.einsum("rkc,ick->ri", xt, wt) + sd[t2i + "linear_fuse.bias"]
+        mid_pre = want.clone()                                                        # input_linear + res: what integration->temporal reads
+        want[1:] += v[1:]
+        want[0] += sd[t2i + "cls_token"].reshape(t, Ci)[ti]
+        assert float((upd - want).abs().max()) < 2e-6                    # the packed operands pass through fp32
+        a2 = torch.cat([rows[:, L["c_x"]:], upd], dim=1)
+        u = a2 @ d["i2t_cat_w"].t() + d["i2t_cat_b"]
+        want_u = lin(mid_pre, "dist_net.integration2temporal_nets.%d.linear_fuse" % i)
+        assert float((u[1:] - want_u[1:]).abs().max()) < 2e-6                       # patch rows only (the class row is never read)
