@@ -43,6 +43,8 @@ CASES = {
     "tiny_scaled": (tiny_arch(), "scaled", 2, "structured"),
     "tiny_a1": (tiny_arch(frames=3, alpha=1, ada_layers=1, selected_layers=[1]), "scaled", 2, "iid"),
     "tiny_a3": (tiny_arch(frames=6, alpha=3, resolution=96, selected_layers=[0, 1]), "scaled", 1, "iid"),
+    # taps skipped between DiST layers, first block untapped, three DiST layers (the hidden block of one layer travels in the next one's operand)
+    "tiny_skip": (tiny_arch(layers=6, selected_layers=[1, 3, 4], frames=8, alpha=2), "scaled", 3, "structured"),
     "b16_8x16_ref": (DistArch(), "reference", 2, "structured"),
     "b16_8x16_scaled": (DistArch(), "scaled", 2, "structured"),
     "b16_8x16_iid": (DistArch(), "reference", 2, "iid"),
