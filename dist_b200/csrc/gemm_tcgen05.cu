@@ -648,6 +648,16 @@ int gemm_tcgen05_launch(const distb200_gemm_desc& d, cudaStream_t stream) {
     // CTA pairs (cta_group::2) halve the L2 -> SM traffic of B; they need an even split of the B tile and enough tiles
     static const int ctas_env = getenv("DISTB200_GEMM_CTAS") ? atoi(getenv("DISTB200_GEMM_CTAS")) : 2;
     args.ctas = (ctas_env == 2 && args.block_n % 32 == 0 && d.groups * row_tiles * args.n_tiles >= 2 * sm_count()) ? 2 : 1;
+    if (args.ctas == 2 && d.impl == DISTB200_IMPL_AUTO) {
+        // Wave quantisation: a pair takes two row tiles of ONE group, so an odd tile count per group leaves half-empty pairs
+        // (IntegrationNetwork's temporal convolution: 13 tiles per clip -> 224 pairs = 3.03 waves of 74).  Fall back to single
+        // CTAs when they fill the machine clearly better.
+        const long long t1 = d.groups * row_tiles * args.n_tiles, t2 = d.groups * ((row_tiles + 1) / 2) * args.n_tiles;
+        const long long u1 = sm_count(), u2 = sm_count() / 2;
+        const double eff1 = (double)t1 / (double)(((t1 + u1 - 1) / u1) * u1);
+        const double eff2 = (double)t1 / (double)(((t2 + u2 - 1) / u2) * u2 * 2);
+        if (eff1 > 1.1 * eff2) args.ctas = 1;
+    }
     if (d.impl == DISTB200_IMPL_TCGEN05_1CTA) args.ctas = 1;
     if (d.impl == DISTB200_IMPL_TCGEN05_2CTA) {
         DISTB200_REQUIRE(args.block_n % 32 == 0, "gemm(tcgen05): CTA pairs need block_n %% 32 == 0 (block_n=%d)", args.block_n);

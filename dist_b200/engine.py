@@ -28,6 +28,20 @@ def _pad8(n):
     return (n + 7) // 8 * 8
 
 
+def block_n_by_waves(rows, n, candidates, units=74):
+    """Column tile of a narrow, epilogue-bound GEMM chosen by wave quantisation: `units` CTA pairs work through
+    ceil(rows / 256) * (n / block_n) tiles; ties go to the wider tile."""
+    best, best_eff = 0, 0.0
+    for bn in sorted(candidates, reverse=True):
+        if n % bn:
+            continue
+        tiles = (rows + 255) // 256 * (n // bn)
+        eff = tiles / float((tiles + units - 1) // units * units)
+        if eff > best_eff + 0.02:
+            best, best_eff = bn, eff
+    return best
+
+
 def kcat_layout(arch):
     """Column layout of the K-concatenated DiST operand buffer (bf16 path), every block on a 128-byte boundary:
     [tap D | hidden activations of the PREVIOUS IntegrationNetwork (ffn Ih | c_fc1 Cm | temporal Cm) | alpha temporal rows |
@@ -570,7 +584,8 @@ class DistEngine:
         hp = hbuf.stride(0)
         self.calls.append(ops.row_stats(upd_a, self.int_st, name="dist.int.stats"))
         self._gemm(upd_a, d["int_wf2"], Ih + Cm, Ci, bias=d["int_bf2"], out=hbuf, ld_out=hp, act=ops.ACT_QUICKGELU, act_to=Ih,
-                   ln_stats=self.int_st, ln_wsum=d["int_ws2"], name="dist.int.fc")
+                   ln_stats=self.int_st, ln_wsum=d["int_ws2"], name="dist.int.fc",
+                   block_n=block_n_by_waves(Mv, Ih + Cm, [bn for bn in (256, 240, 192, 160, 128) if (Ih + Cm) % bn == 0]))
         self._gemm(hbuf[:, Ih:], d["tf2_w"], Cm, Cm, a_dim=(Cm, t * N, b, 1), a_stride=(1, hp, t * N * hp, Mv * hp),
                    taps=[((k - half) * N, 0, 0) for k in range(a.t_kernel)], b_tap_stride=Cm * Cm, ldb=Cm,
                    groups=b, rows_per_group=t * N, bias=d["tf2_b"], out=hbuf[:, Ih + Cm:], ld_out=hp, act=ops.ACT_QUICKGELU,
