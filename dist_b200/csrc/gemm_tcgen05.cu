@@ -682,7 +682,11 @@ int gemm_tcgen05_launch(const distb200_gemm_desc& d, cudaStream_t stream) {
     const uint32_t stage_bytes = (A_STAGE_BYTES + args.b_stage_bytes) * (uint32_t)args.kpack;
     // epilogue width: long reductions want the deepest operand ring, everything else the better latency hiding
     static const int ew_env = getenv("DISTB200_GEMM_EPI_WARPS") ? atoi(getenv("DISTB200_GEMM_EPI_WARPS")) : 0;
-    const int ew = ew_env == 8 || ew_env == 12 ? ew_env : ((long long)d.k * d.num_taps >= 2048 ? 8 : 12);
+    // Measured per call site (B/16, 32 clips): 8 warps (double-buffered residual prefetch, deeper operand ring) also win for the
+    // plain single-tap GEMMs from K = 768 up (out_proj 1.40 -> 1.34 ms, qkv 1.64 -> 1.62, DiST input GEMM 0.92 -> 0.89), while
+    // QuickGELU epilogues (FC1 2.41 vs 2.53) and the tapped convolutions ((1,3,3): 0.62 vs 0.86) need the 12.
+    const bool plain = d.num_taps == 1 && d.act == DISTB200_ACT_NONE && d.k >= 768;
+    const int ew = ew_env == 8 || ew_env == 12 ? ew_env : (((long long)d.k * d.num_taps >= 2048 || plain) ? 8 : 12);
     DISTB200_REQUIRE(!d.stat_partials || args.n_tiles * (ew / 4) <= DISTB200_STAT_SLOTS,
                     "gemm(tcgen05): %d column tiles x %d epilogue phases exceed the %d statistic slots", args.n_tiles, ew / 4, DISTB200_STAT_SLOTS);
     args.stages = smem_budget(ew) / (int)stage_bytes;
