@@ -119,7 +119,7 @@ def temporal_stem(sd, video, ps):
     b, _, T, H, W = video.shape
     g = H // ps
     pat = patchify(video.permute(0, 2, 1, 3, 4).reshape(-1, 3, H, W), ps).view(b, T, g * g, -1)
-    out = torch.zeros(b, T, g * g, Ct, dtype=video.dtype)
+    out = torch.zeros(b, T, g * g, Ct, dtype=video.dtype, device=video.device)
     for k in range(kt):
         shift = k - kt // 2                      # output frame tau reads input frame tau + shift
         lo, hi = max(0, -shift), min(T, T - shift)
@@ -137,14 +137,14 @@ def temporal_net(sd, prefix, x):
     y = _ln(x, sd[prefix + ".ln.weight"], sd[prefix + ".ln.bias"])
     w1, b1 = sd[prefix + ".temporal_net.c_fc1.weight"], sd[prefix + ".temporal_net.c_fc1.bias"]
     kt = w1.shape[2]
-    z = torch.zeros(b, T, g, g, w1.shape[0], dtype=x.dtype)
+    z = torch.zeros(b, T, g, g, w1.shape[0], dtype=x.dtype, device=x.device)
     for k in range(kt):
         s = k - kt // 2
         lo, hi = max(0, -s), min(T, T - s)
         z[:, lo:hi] += y[:, lo + s:hi + s] @ w1[:, :, k, 0, 0].t()
     z = _qgelu(z + b1)
     w2, b2 = sd[prefix + ".temporal_net.c_fc2.weight"], sd[prefix + ".temporal_net.c_fc2.bias"]
-    o = torch.zeros(b, T, g, g, w2.shape[0], dtype=x.dtype)
+    o = torch.zeros(b, T, g, g, w2.shape[0], dtype=x.dtype, device=x.device)
     for i in range(3):
         for j in range(3):
             di, dj = i - 1, j - 1
