@@ -149,7 +149,7 @@ def test_softce_head(batch, E, C):
     ls = torch.sum(-target.double() * torch.log_softmax(lg, dim=-1), dim=-1).mean()
     ls.backward()
     assert rel_l2(logits, lg.detach()) < 1e-5
-    assert abs(float(loss) - float(ls)) < 1e-5 * abs(float(ls))
+    assert abs(float(loss) - float(ls.detach())) < 1e-5 * abs(float(ls.detach()))
     assert rel_l2(d_emb, e.grad) < 2e-5
 
 
