@@ -117,6 +117,23 @@ __device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
     asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// Cluster-scope release / acquire pair for operands that THREADS of the peer CTA wrote into the peer's shared memory and that
+// the pair MMA (issued by the leader) makes the peer's tensor core read (the fused TemporalNet kernel).
+__device__ __forceinline__ void mbar_arrive_release_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_acquire_cluster(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.b32 %0, 1, 0, p;\n\t}\n"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
 // TMA loads of a CTA pair: data lands in the issuing CTA's shared memory, the bytes are counted on the barrier at
 // `bar` (a shared::cluster address, normally the leader CTA's)
 __device__ __forceinline__ void tma_load_4d_2sm(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, int c2, int c3) {
@@ -190,6 +207,20 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
     d |= (uint64_t)(1024 >> 4) << 32;   // stride byte offset between 8-row groups
     d |= (uint64_t)1 << 46;             // descriptor version (Blackwell)
     d |= (uint64_t)2 << 61;             // SWIZZLE_128B
+    return d;
+}
+
+// K-major operand tile WITHOUT swizzle (cute::UMMA::LayoutType::INTERLEAVE): core matrices of 8 rows x 16 bytes, the rows of
+// a core matrix 16 bytes apart; LBO = distance between the two core matrices of one K = 16 step, SBO = distance between
+// 8-row groups.  With SBO = 128 the byte address of row r in k-chunk kc is  base + kc * LBO + r * 16  - linear in r, so a
+// descriptor whose start address is moved by s * 16 bytes addresses the operand shifted by s rows (any s, not only
+// multiples of 8).  The fused TemporalNet kernel serves the nine taps of the (1,3,3) convolution that way.
+__device__ __forceinline__ uint64_t umma_desc_k_nosw(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+    d |= (uint64_t)1 << 46;             // descriptor version (Blackwell); layout type 0 = no swizzle
     return d;
 }
 

@@ -61,6 +61,18 @@ class WgradDesc(C.Structure):
     ]
 
 
+class TemporalNetDesc(C.Structure):
+    """Mirror of ``distb200_temporalnet_desc``."""
+    _fields_ = [
+        ("x", C.c_void_p), ("u", C.c_void_p), ("alpha", C.c_int32), ("dtype", C.c_int32),
+        ("ln_g", C.c_void_p), ("ln_b", C.c_void_p), ("w1", C.c_void_p), ("b1", C.c_void_p), ("w2", C.c_void_p), ("b2", C.c_void_p),
+        ("out", C.c_void_p), ("out2", C.c_void_p), ("ld_out2", C.c_int64),
+        ("out2_gdiv", C.c_int32), ("out2_cstep", C.c_int32), ("out2_gstride", C.c_int64), ("out2_roff", C.c_int64),
+        ("clips", C.c_int32), ("frames", C.c_int32), ("grid", C.c_int32), ("channels", C.c_int32),
+        ("eps", C.c_float), ("max_ctas", C.c_int32),
+    ]
+
+
 _LIB = None
 
 
@@ -90,6 +102,7 @@ def lib():
     L.distb200_arch.restype = C.c_int
     L.distb200_last_error.restype = C.c_char_p
     L.distb200_gemm.argtypes = [C.POINTER(GemmDesc), vp]
+    L.distb200_temporalnet.argtypes = [C.POINTER(TemporalNetDesc), vp]
     L.distb200_layernorm.argtypes = [vp, i64, vp, i64, i64, i64, i32, f32, vp, vp, vp, i64, vp, vp, vp, i64, i32, vp]
     L.distb200_row_stats.argtypes = [vp, i32, i64, i64, i32, f32, vp, vp]
     L.distb200_row_stats_finalize.argtypes = [vp, i64, i32, f32, vp, vp]
@@ -121,7 +134,7 @@ def lib():
     for name in TRAIN_EXPORTS:
         getattr(L, name).restype = C.c_int
     for name in ("row_stats", "gemm", "layernorm", "attention", "cross_attention", "patchify", "patchify_u8", "rows_bcast", "mean_rows", "class_head", "view_ensemble",
-                 "topk_correct", "attention_causal", "embed_tokens", "gather_eot", "row_stats_finalize"):
+                 "topk_correct", "attention_causal", "embed_tokens", "gather_eot", "row_stats_finalize", "temporalnet"):
         getattr(L, "distb200_" + name).restype = C.c_int
     assert L.distb200_version() == 100 and L.distb200_arch() == 100
     _LIB = L
@@ -135,7 +148,7 @@ TRAIN_EXPORTS = ("distb200_gemm_wgrad", "distb200_quickgelu", "distb200_quickgel
 EXPORTS = TRAIN_EXPORTS + ("distb200_version", "distb200_arch", "distb200_last_error", "distb200_gemm", "distb200_row_stats", "distb200_layernorm",
            "distb200_attention", "distb200_cross_attention", "distb200_patchify", "distb200_patchify_u8", "distb200_view_ensemble", "distb200_topk_correct", "distb200_rows_bcast",
            "distb200_mean_rows", "distb200_class_head", "distb200_attention_causal", "distb200_embed_tokens", "distb200_gather_eot",
-           "distb200_row_stats_finalize")
+           "distb200_row_stats_finalize", "distb200_temporalnet")
 
 
 class DistB200Error(RuntimeError):
@@ -231,6 +244,31 @@ def gemm(a, b, n, k, *, a_dim=None, a_stride=None, taps=((0, 0, 0),), b_tap_stri
     if res is not None:
         nbytes += rows * int(n) * 4 * int(out_rep)
     return Call(lib().distb200_gemm, (C.byref(d),), name, keep=(d, a, b, bias, res, out, out2, ln_stats, ln_wsum, stat_partials), flops=flops, nbytes=nbytes)
+
+
+def temporalnet(x, ln_g, ln_b, w1, b1, w2, b2, *, clips, frames, grid, u=None, alpha=1, out=None, out2=None, ld_out2=0,
+                out2_gdiv=0, out2_cstep=0, out2_gstride=0, out2_roff=0, eps=1e-5, max_ctas=0, name="temporalnet"):
+    """Prepare one fused TemporalNet block (``distb200_temporalnet``; dist.py:48-65 + the i2t add of dist.py:231).
+
+    ``x`` fp32 ``[clips, frames, grid*grid, C]`` channels-last, ``w1`` bf16 ``[3, C, C]``, ``w2`` bf16 ``[9, C, C]`` (per-tap K-major),
+    ``u`` optional fp32 ``[clips, frames/alpha, grid*grid, C]``."""
+    ch = int(w1.shape[-1])
+    assert x.dtype == torch.float32 and w1.dtype == w2.dtype == torch.bfloat16
+    assert tuple(w1.shape) == (3, ch, ch) and tuple(w2.shape) == (9, ch, ch) and w1.is_contiguous() and w2.is_contiguous()
+    assert u is None or u.dtype == torch.float32
+    assert out is None or out.dtype == torch.float32
+    assert out2 is None or out2.dtype == torch.bfloat16
+    d = TemporalNetDesc()
+    d.x, d.u, d.alpha, d.dtype = x.data_ptr(), _ptr(u), int(alpha), BF16
+    d.ln_g, d.ln_b, d.w1, d.b1, d.w2, d.b2 = ln_g.data_ptr(), ln_b.data_ptr(), w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr()
+    d.out, d.out2, d.ld_out2 = _ptr(out), _ptr(out2), int(ld_out2 if out2 is not None else 0)
+    d.out2_gdiv, d.out2_cstep, d.out2_gstride, d.out2_roff = int(out2_gdiv), int(out2_cstep), int(out2_gstride), int(out2_roff)
+    d.clips, d.frames, d.grid, d.channels = int(clips), int(frames), int(grid), ch
+    d.eps, d.max_ctas = float(eps), int(max_ctas)
+    rows = int(clips) * int(frames) * int(grid) * int(grid)
+    flops = 2 * rows * ch * ch * 12
+    nbytes = rows * ch * (4 + (4 if out is not None else 0) + (2 if out2 is not None else 0)) + (rows // int(alpha) * ch * 4 if u is not None else 0)
+    return Call(lib().distb200_temporalnet, (C.byref(d),), name, keep=(d, x, u, ln_g, ln_b, w1, b1, w2, b2, out, out2), flops=flops, nbytes=nbytes)
 
 
 def layernorm(x, g1, b1, y1, *, in2=None, in2_period=1, g2=None, b2=None, y2=None, rows=None, cols=None,

@@ -131,6 +131,56 @@ typedef struct distb200_gemm_desc {
 
 int distb200_gemm(const distb200_gemm_desc* desc, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * distb200_temporalnet - one fused TemporalNet block (models/module_zoo/branches/dist.py:48-65) on the
+ * channels-last temporal stream, with the integration->temporal add of the PREVIOUS DiST layer
+ * (dist.py:231, nearest upsample over alpha dense frames, dist.py:105) folded into its input:
+ *
+ *     xe[b,tau,p,:] = x[b,tau,p,:] + (u ? u[b, tau / alpha, p, :] : 0)                    p = r*g + c, r,c < g
+ *     y             = LayerNorm_C(xe) * ln_g + ln_b                     (eps, biased variance; dist.py:65, clip.py:181-187)
+ *     z[b,tau,p,:]  = q( sum_{k<3}   y[b, tau+k-1, p, :] . w1[k]^T + b1 )                 zero outside 0 <= tau+k-1 < T
+ *     o[b,tau,p,:]  = sum_{i,j<3} z[b, tau, (r+i-1)*g + (c+j-1), :] . w2[3i+j]^T + b2      zero outside the g x g frame
+ *     out[b,tau,p,:] = q( xe + o )                                      q(v) = v * sigmoid(1.702 v), clip.py:199-201
+ *
+ * w1 [3][C][C] / w2 [9][C][C] are the per-tap K-major matrices distb200_gemm takes for the same convolutions
+ * (w1[k][n][c] = temporal_net.c_fc1.weight[n,c,k,0,0], w2[3i+j][n][c] = c_fc2.weight[n,c,0,i,j]).
+ * out (fp32, may be NULL; must not alias x) receives the new stream; out2 (bf16, may be NULL) the operand copy, placed
+ * like distb200_gemm_desc.out2 with groups = frames: with out2_gdiv = a > 0 the copy of frame f = b*T + tau, position p
+ * goes to row (f / a) * out2_gstride + out2_roff + p, column (f % a) * out2_cstep (+ channel), row pitch ld_out2;
+ * out2_gdiv = 0 places it at row f * g*g + p.
+ *
+ * One launch replaces distb200_layernorm + two tapped distb200_gemm calls (+ the read-modify-write of the i2t add):
+ * a CTA pair (cta_group::2, both weight sets resident in shared memory, split between the pair) walks bands of image rows
+ * frame by frame; LayerNorm'd frames live in a three-slot ring of un-swizzled K-major shared-memory tiles, z stays in
+ * shared memory in a zero-padded (g+2)-pitch layout so that the nine spatial taps are nine row-shifted descriptors of ONE
+ * tile, both accumulators live in TMEM.  bf16 operands / fp32 accumulation only (dtype = DISTB200_BF16); the fp32 parity
+ * path composes the same block from distb200_layernorm + distb200_gemm.
+ * Constraints: C in {32, 64, 96}; g <= 60; 16-byte aligned pointers; ld_out2 and out2_cstep multiples of 8. */
+typedef struct distb200_temporalnet_desc {
+    const float* x;
+    const float* u;                /* optional addend [clips, frames / alpha, g*g, C] fp32 */
+    int32_t alpha;                 /* >= 1 (ignored when u is NULL) */
+    int32_t dtype;                 /* operand dtype of w1 / w2 / out2: DISTB200_BF16 */
+    const float* ln_g;
+    const float* ln_b;
+    const void* w1;
+    const float* b1;
+    const void* w2;
+    const float* b2;
+    float* out;
+    void*  out2;
+    int64_t ld_out2;
+    int32_t out2_gdiv;
+    int32_t out2_cstep;
+    int64_t out2_gstride;
+    int64_t out2_roff;
+    int32_t clips, frames, grid, channels;
+    float   eps;
+    int32_t max_ctas;              /* 0 = one CTA per SM; otherwise an upper bound on the (even) CTA count */
+} distb200_temporalnet_desc;
+
+int distb200_temporalnet(const distb200_temporalnet_desc* desc, void* stream);
+
 /* LayerNorm over the last dim (eps, biased variance; clip.py:181-187) of x = in1 (+ in2[row % in2_period]),
  * fp32 statistics.  Writes y1 = xhat*g1+b1 and, when y2 != NULL, y2 = xhat*g2+b2 (two affine views of the
  * same statistics: dist.py:43-45 ln / ln_temporal).  y may alias in1 when out_dtype is fp32.

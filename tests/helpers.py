@@ -58,3 +58,21 @@ def wgrad_reference(a4, a_dim, taps, dy, groups, rpg, img_w=0, group_dim=2):
     """dw[j, n, k] = sum_rows dy[row, n] * A_j(row, k) in fp64; dy [groups*rpg, n] in output-row order."""
     K = a_dim[0]
     return torch.stack([dy.double().t() @ gather_rows(a4, a_dim, tap, groups, rpg, img_w, group_dim)[:, :K] for tap in taps])
+
+
+def temporalnet_reference(x, u, alpha, gam, bet, w1, b1, w2, b2, emulate_bf16):
+    """Definition of ``distb200_temporalnet`` (include/distb200.h) with torch's own convolutions, any float dtype.
+    x [B,T,g,g,C]; u [B,T/alpha,g,g,C] or None; w1 [3,C,C] / w2 [9,C,C] as (tap, out, in).  ``emulate_bf16`` rounds the two MMA
+    operands (LayerNorm output, first activation) to bf16 like the kernel.  tests/test_oracle.py ties it to the oracle's
+    ``temporal_net`` (dist.py:48-65)."""
+    import torch.nn.functional as F
+    q = lambda v: v * torch.sigmoid(1.702 * v)
+    r = (lambda t: t.to(torch.bfloat16).to(t.dtype)) if emulate_bf16 else (lambda t: t)
+    xe = x if u is None else x + u.repeat_interleave(alpha, dim=1)
+    C = x.shape[-1]
+    y = r(F.layer_norm(xe, (C,), gam, bet, 1e-5)).permute(0, 4, 1, 2, 3)      # [B,C,T,g,g]
+    k1 = w1.permute(1, 2, 0)[:, :, :, None, None]                            # [Cout,Cin,3,1,1]
+    z = r(q(F.conv3d(y, k1, b1, padding=(1, 0, 0))))
+    k2 = w2.reshape(3, 3, C, C).permute(2, 3, 0, 1)[:, :, None]              # [Cout,Cin,1,3,3]
+    o = F.conv3d(z, k2, b2, padding=(0, 1, 1)).permute(0, 2, 3, 4, 1)
+    return q(xe + o)
