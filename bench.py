@@ -181,6 +181,8 @@ def family(call):
     n = call.name
     if n.startswith("patchify"):
         return "patchify"
+    if n == "dist.tn":
+        return "temporalnet"
     if "attention" in n or n.endswith(".attn"):
         return "attention" if n.startswith("vit") else "cross_attention"
     if n.endswith((".ln", ".ln_1", ".ln_2", ".ln_pre", ".ln_kv", ".ln_q", ".ln_out", "ln_post", ".stats")) or ".ln" in n:

@@ -335,6 +335,14 @@ class DistEngine:
                 self.stat_p = [z(Mv, ops.STAT_SLOTS, 2, dtype=f32), z(Mv, ops.STAT_SLOTS, 2, dtype=f32)]
         self._hb_prev = None
         self.xT = z(Mt, Ct, dtype=f32)
+        # Fused TemporalNet (distb200_temporalnet, bf16 path): LayerNorm + both convolutions + residual in one launch, the
+        # integration->temporal add of the previous layer folded into its input.  The stream ping-pongs between two buffers (a frame's
+        # neighbours are read while it is written) and the i2t GEMM only writes its [b*t*P, Ct] result `u`.
+        self.tn_fused = (self.kcat and os.environ.get("DISTB200_TN_FUSED", "1") != "0" and Ct in (32, 64, 96)
+                         and a.temporal_hidden == Ct and a.t_kernel == 3 and 128 // a.grid - 2 >= 1)
+        if self.tn_fused:
+            self.xTs = [self.xT, z(Mt, Ct, dtype=f32)]
+            self.u_i2t = z(F * P, Ct)
         self.xT_a = z(Mt, Ct)
         self.xln = z(Mt, Ct)
         self.y1 = z(Mt, a.temporal_hidden)
@@ -508,6 +516,9 @@ class DistEngine:
         add = self.calls.append
         half = a.t_kernel // 2
 
+        if self.kcat and self.tn_fused:
+            self._plan_dist_layer_kcat(i, None)
+            return
         # ---- TemporalNet (dist.py:48-65) ----
         self._ln(self.xT, d["tn_ln"], self.xln, name="dist.tn.ln")
         self._gemm(self.xln, d["tn_w1"], Ch, Ct, a_dim=(Ct, T * P, b, 1), a_stride=(1, Ct, T * P * Ct, Mt * Ct),
@@ -567,17 +578,29 @@ class DistEngine:
         L, tw = self.kl, self.tw
         buf = self.tapw[sel[i] % 2]
         upd_a = buf[:, L["c_u"]:L["c_u"] + Ci]
-        # TemporalNet's (1,3,3) convolution drops the bf16 copy of dense frame alpha*ti + k next to token row 1 + r of sparse frame ti
-        self._gemm(self.y1, d["tn_w2"], Ct, a.temporal_hidden, out2=buf[:, L["c_x"]:], ld_out2=tw, out2_gdiv=al, out2_cstep=Ct, out2_gstride=N,
-                   out2_roff=1, **conv_s)
+        # TemporalNet drops the bf16 copy of dense frame alpha*ti + k next to token row 1 + r of sparse frame ti
+        if self.tn_fused:
+            # dist.py:48-65 in one launch; x = stream of the previous layer + its integration->temporal term (dist.py:231).  The last
+            # layer's fp32 stream is read by nothing (only its bf16 copy feeds the temporal->integration columns).
+            self.calls.append(ops.temporalnet(
+                self.xTs[i % 2], d["tn_ln"][0], d["tn_ln"][1], d["tn_w1"], d["tn_b1"], d["tn_w2"], d["tn_b2"], clips=b, frames=T, grid=a.grid,
+                u=self.u_i2t if i > 0 else None, alpha=al, out=None if last else self.xTs[(i + 1) % 2], out2=buf[:, L["c_x"]:], ld_out2=tw,
+                out2_gdiv=al, out2_cstep=Ct, out2_gstride=N, out2_roff=1, name="dist.tn"))
+        else:
+            self._gemm(self.y1, d["tn_w2"], Ct, a.temporal_hidden, out2=buf[:, L["c_x"]:], ld_out2=tw, out2_gdiv=al, out2_cstep=Ct, out2_gstride=N,
+                       out2_roff=1, **conv_s)
         # upd in ONE pass: input_linear + previous IntegrationNetwork's output projection + temporal->integration + cls token
         self._gemm(buf, d["cat_w"], Ci, L["c_u"], bias=d["cat_b"], out=self.mid, ld_out=Ci, out2=upd_a, ld_out2=tw, name="dist.input_linear")
         # integration -> temporal on the pre-fusion stream mid = upd - t2i(xT) (dist.py:99-105,231); dead in the last layer
         if not last:
             k2 = L["c_u"] + Ci - L["c_x"]
-            self._gemm(buf[:, L["c_x"]:], d["i2t_cat_w"], Ct, k2, a_dim=(k2, N, F, 1), a_stride=(1, tw, N * tw, Mv * tw), taps=[(1, 0, 0)],
-                       groups=F, rows_per_group=P, ldb=k2, bias=d["i2t_cat_b"], res=self.xT, ld_res=Ct, res_gstride=al * P,
-                       res_rep_stride=P, out=self.xT, ld_out=Ct, out_gstride=al * P, out_rep=al, out_rep_stride=P, name="dist.i2t")
+            i2t = dict(a_dim=(k2, N, F, 1), a_stride=(1, tw, N * tw, Mv * tw), taps=[(1, 0, 0)], groups=F, rows_per_group=P, ldb=k2,
+                       bias=d["i2t_cat_b"], name="dist.i2t")
+            if self.tn_fused:      # the nearest upsample + add happens in the next layer's TemporalNet
+                self._gemm(buf[:, L["c_x"]:], d["i2t_cat_w"], Ct, k2, out=self.u_i2t, ld_out=Ct, **i2t)
+            else:
+                self._gemm(buf[:, L["c_x"]:], d["i2t_cat_w"], Ct, k2, res=self.xT, ld_res=Ct, res_gstride=al * P, res_rep_stride=P,
+                           out=self.xT, ld_out=Ct, out_gstride=al * P, out_rep=al, out_rep_stride=P, **i2t)
         # IntegrationNetwork (dist.py:16-45), both LayerNorms folded; its hidden block lands next to the NEXT layer's tap, where that
         # layer's first GEMM applies the output projection (the last layer projects here: the ada-pooling head reads `res`)
         hbuf = self.int_w if last else self.tapw[sel[i + 1] % 2][:, L["c_h"]:]

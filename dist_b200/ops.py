@@ -251,11 +251,11 @@ def temporalnet(x, ln_g, ln_b, w1, b1, w2, b2, *, clips, frames, grid, u=None, a
     """Prepare one fused TemporalNet block (``distb200_temporalnet``; dist.py:48-65 + the i2t add of dist.py:231).
 
     ``x`` fp32 ``[clips, frames, grid*grid, C]`` channels-last, ``w1`` bf16 ``[3, C, C]``, ``w2`` bf16 ``[9, C, C]`` (per-tap K-major),
-    ``u`` optional fp32 ``[clips, frames/alpha, grid*grid, C]``."""
+    ``u`` optional bf16 ``[clips, frames/alpha, grid*grid, C]``."""
     ch = int(w1.shape[-1])
     assert x.dtype == torch.float32 and w1.dtype == w2.dtype == torch.bfloat16
     assert tuple(w1.shape) == (3, ch, ch) and tuple(w2.shape) == (9, ch, ch) and w1.is_contiguous() and w2.is_contiguous()
-    assert u is None or u.dtype == torch.float32
+    assert u is None or u.dtype == torch.bfloat16
     assert out is None or out.dtype == torch.float32
     assert out2 is None or out2.dtype == torch.bfloat16
     d = TemporalNetDesc()
@@ -267,7 +267,7 @@ def temporalnet(x, ln_g, ln_b, w1, b1, w2, b2, *, clips, frames, grid, u=None, a
     d.eps, d.max_ctas = float(eps), int(max_ctas)
     rows = int(clips) * int(frames) * int(grid) * int(grid)
     flops = 2 * rows * ch * ch * 12
-    nbytes = rows * ch * (4 + (4 if out is not None else 0) + (2 if out2 is not None else 0)) + (rows // int(alpha) * ch * 4 if u is not None else 0)
+    nbytes = rows * ch * (4 + (4 if out is not None else 0) + (2 if out2 is not None else 0)) + (rows // int(alpha) * ch * 2 if u is not None else 0)
     return Call(lib().distb200_temporalnet, (C.byref(d),), name, keep=(d, x, u, ln_g, ln_b, w1, b1, w2, b2, out, out2), flops=flops, nbytes=nbytes)
 
 

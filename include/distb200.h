@@ -158,7 +158,7 @@ int distb200_gemm(const distb200_gemm_desc* desc, void* stream);
  * Constraints: C in {32, 64, 96}; g <= 60; 16-byte aligned pointers; ld_out2 and out2_cstep multiples of 8. */
 typedef struct distb200_temporalnet_desc {
     const float* x;
-    const float* u;                /* optional addend [clips, frames / alpha, g*g, C] fp32 */
+    const void* u;                 /* optional addend [clips, frames / alpha, g*g, C] in `dtype` (bf16: the i2t GEMM's output) */
     int32_t alpha;                 /* >= 1 (ignored when u is NULL) */
     int32_t dtype;                 /* operand dtype of w1 / w2 / out2: DISTB200_BF16 */
     const float* ln_g;

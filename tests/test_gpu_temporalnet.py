@@ -21,6 +21,7 @@ CASES = {
     "b16_long_runs": (96, 14, 8, 5, 2, True, 6),
     "l14": (96, 16, 8, 2, 4, True, 0),
     "l14_nou": (96, 16, 5, 3, 1, False, 10),
+    "g22_short_last_band": (32, 22, 3, 1, 1, True, 0),      # bands of 4,3,...: rows past a short band must never be addressed
 }
 
 
@@ -31,7 +32,7 @@ def test_temporalnet(name):
     gen = torch.Generator().manual_seed(sum(map(ord, name)))
     P = g * g
     x = torch.randn(B, T, g, g, C, generator=gen) * 1.5 + 0.3
-    u = torch.randn(B, T // alpha, g, g, C, generator=gen) * 0.5 if with_u else None
+    u = (torch.randn(B, T // alpha, g, g, C, generator=gen) * 0.5).to(torch.bfloat16) if with_u else None
     gam, bet = 1 + 0.2 * torch.randn(C, generator=gen), 0.2 * torch.randn(C, generator=gen)
     w1 = torch.randn(3, C, C, generator=gen) / (3 * C) ** 0.5
     w2 = torch.randn(9, C, C, generator=gen) / (9 * C) ** 0.5 * 2
