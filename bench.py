@@ -196,8 +196,9 @@ def family(call):
     return "gemm_vit" if n.startswith("vit.") else "gemm_dist"
 
 
-def run_train(args, arch, wl, world, rank, local, dev):
-    """Fine-tuning step (frozen CLIP forward, DiST forward + backward, flat NCCL gradient all-reduce, AdamW)."""
+def run_train(args, arch, wl, world, rank, local, dev, light=False):
+    """Fine-tuning step (frozen CLIP forward, DiST forward + backward, flat NCCL gradient all-reduce, AdamW).
+    Returns the JSON line (rank 0) or None; ``light`` = the compact sub-record of the default run (no end-to-end leg)."""
     import torch.distributed as dist
     from dist_b200.train import TrainEngine
     sd = synth.synth_state_dict(arch, seed=0, init="reference")
@@ -239,40 +240,42 @@ def run_train(args, arch, wl, world, rank, local, dev):
     clocks = sampler.stop() if rank == 0 else None
     value = world * b * args.steps / (total_ms / 1e3)
 
-    # end to end: pinned host clips + soft targets in, loss out, every step.  The clips of step i+1 cross PCIe on a copy stream
-    # while step i computes (a pin_memory loader with .cuda(non_blocking=True), runs/train.py:87-89); every step's H2D copies
-    # and the D2H read of the loss are inside the timed region.
-    host = [clips.clone().pin_memory(), clips.flip(0).clone().pin_memory()]
-    host_t = target.clone().pin_memory()
-    loss_host = torch.empty(1).pin_memory()
-    copy_stream = torch.cuda.Stream(dev)
-    dev_buf = [torch.empty_like(d_clips) for _ in range(2)]
-    dev_tgt = [torch.empty_like(d_target) for _ in range(2)]
-    ready = [torch.cuda.Event() for _ in range(2)]
-    consumed = [torch.cuda.Event() for _ in range(2)]
+    ems = None
+    if not light:
+        # end to end: pinned host clips + soft targets in, loss out, every step.  The clips of step i+1 cross PCIe on a copy stream
+        # while step i computes (a pin_memory loader with .cuda(non_blocking=True), runs/train.py:87-89); every step's H2D copies
+        # and the D2H read of the loss are inside the timed region.
+        host = [clips.clone().pin_memory(), clips.flip(0).clone().pin_memory()]
+        host_t = target.clone().pin_memory()
+        loss_host = torch.empty(1).pin_memory()
+        copy_stream = torch.cuda.Stream(dev)
+        dev_buf = [torch.empty_like(d_clips) for _ in range(2)]
+        dev_tgt = [torch.empty_like(d_target) for _ in range(2)]
+        ready = [torch.cuda.Event() for _ in range(2)]
+        consumed = [torch.cuda.Event() for _ in range(2)]
 
-    def prefetch(i):
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(consumed[i & 1])
-            dev_buf[i & 1].copy_(host[i & 1], non_blocking=True)
-            dev_tgt[i & 1].copy_(host_t, non_blocking=True)
-            ready[i & 1].record(copy_stream)
+        def prefetch(i):
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(consumed[i & 1])
+                dev_buf[i & 1].copy_(host[i & 1], non_blocking=True)
+                dev_tgt[i & 1].copy_(host_t, non_blocking=True)
+                ready[i & 1].record(copy_stream)
 
-    for ev in consumed:
-        ev.record(torch.cuda.current_stream())
-    prefetch(0)
+        for ev in consumed:
+            ev.record(torch.cuda.current_stream())
+        prefetch(0)
 
-    def e2e_step(i):
-        prefetch(i + 1)
-        torch.cuda.current_stream().wait_event(ready[i & 1])
-        loss = eng.train_step(dev_buf[i & 1], dev_tgt[i & 1], lr)
-        consumed[i & 1].record(torch.cuda.current_stream())
-        loss_host.copy_(loss, non_blocking=False)
+        def e2e_step(i):
+            prefetch(i + 1)
+            torch.cuda.current_stream().wait_event(ready[i & 1])
+            loss = eng.train_step(dev_buf[i & 1], dev_tgt[i & 1], lr)
+            consumed[i & 1].record(torch.cuda.current_stream())
+            loss_host.copy_(loss, non_blocking=False)
 
-    for i in range(2):
-        e2e_step(i)
-    ems, ewall = timed(e2e_step, args.steps)
-    ems = max(ems, ewall)
+        for i in range(2):
+            e2e_step(i)
+        ems, ewall = timed(e2e_step, args.steps)
+        ems = max(ems, ewall)
     if rank == 0:
         pk = peaks()
         fwd_fl, bwd_fl = sum(c.flops for c in eng.calls), sum(c.flops for c in eng.bwd)
@@ -285,16 +288,18 @@ def run_train(args, arch, wl, world, rank, local, dev):
                        "clips_per_gpu": b, "precision": args.precision, "cuda_graph": "forward + backward", "optimizer": "AdamW lr 3.2e-4 wd 1e-4",
                        "gflop_per_clip": round((fwd_fl + bwd_fl) / b / 1e9, 1)},
             "model_tflops": value / world * (fwd_fl + bwd_fl) / b / 1e12,
-            "e2e": {"value": world * b * args.steps / (ems / 1e3), "unit": "clips/s", "h2d_bytes_per_step": int(clips.numel() * 4 + target.numel() * 4),
-                    "d2h_bytes_per_step": 4, "ms_per_step": ems / args.steps},
+            "e2e": None if ems is None else {"value": world * b * args.steps / (ems / 1e3), "unit": "clips/s",
+                                             "h2d_bytes_per_step": int(clips.numel() * 4 + target.numel() * 4), "d2h_bytes_per_step": 4,
+                                             "ms_per_step": ems / args.steps},
             "gpu_launches": (len(eng.calls) + len(eng.bwd) + len(eng.pack_calls) + 2) * args.steps,
             "launches_per_step": len(eng.calls) + len(eng.bwd) + len(eng.pack_calls) + 2, "loss": float(eng.loss), "clocks": clocks,
             "peaks": {"bf16_tflops_sustained": pk["tf_sustained"], "hbm_gbs": pk["hbm"]},
         }
-        print(json.dumps(line))
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    else:
+        line = None
+    del eng
+    torch.cuda.empty_cache()
+    return line
 
 
 def main():
@@ -308,6 +313,7 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="headline workload only (skip the compact sub-records of the other BASELINE configs)")
     ap.add_argument("--mode", default="infer", choices=["infer", "train"],
                     help="train = one fine-tuning step per step (BASELINE configs[4]; use --workload b16_16x32)")
     args = ap.parse_args()
@@ -329,9 +335,38 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     if args.mode == "train":
-        run_train(args, arch, wl, world, rank, local, dev)
-        return
+        line = run_train(args, arch, wl, world, rank, local, dev)
+    else:
+        line = run_infer(args, arch, wl, world, rank, local, dev)
+        if not args.no_extra and args.workload == "b16_8x16":
+            # The other BASELINE.json configs as compact sub-records of the same run (same ranks, same clocks): the long-stack
+            # B/16, ViT-L/14 (configs[2,3], the second half of the metric) and the fine-tuning step (configs[4]).
+            import copy
+            extra = {}
+            for name, mode, steps, warm in (("b16_32x64", "infer", 6, 3), ("l14_32x64", "infer", 4, 3), ("b16_16x32", "train", 6, 3)):
+                a2 = copy.copy(args)
+                a2.workload, a2.steps, a2.warmup, a2.no_e2e, a2.no_cpu_baseline = name, steps, warm, True, True
+                wl2 = WORKLOADS[name]
+                arch2 = DistArch(**wl2["arch"]).validate()
+                fn = run_train if mode == "train" else run_infer
+                sub = fn(a2, arch2, wl2, world, rank, local, dev, light=True)
+                if sub is not None:
+                    keep = ("value", "unit", "ms_per_step", "steps", "warmup", "dtype", "model_tflops", "roofline", "roofline_hbm", "gemm_all",
+                            "launches_per_step", "clocks", "loss")
+                    extra[("train_" if mode == "train" else "") + name] = dict({k: sub[k] for k in keep if k in sub}, workload=sub["config"]["workload"])
+            if line is not None:
+                line["workloads"] = extra
+    if rank == 0 and line is not None:
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
 
+
+def run_infer(args, arch, wl, world, rank, local, dev, light=False):
+    """Inference throughput of one workload.  Returns the JSON line (rank 0) or None; ``light`` = compact sub-record (no end-to-end
+    leg, no CPU baseline)."""
+    import torch.distributed as dist
     from dist_b200.engine import DistEngine
     sd = synth.synth_state_dict(arch, seed=0, init="reference")
     text = synth.synth_text_features(arch.num_classes, arch.embed_dim)
@@ -344,11 +379,28 @@ def main():
     eng.video.copy_(clips)
     eng.capture()
     gathered = torch.empty(world * b, eng.probs.shape[1], device=dev) if world > 1 else None
+    # The logits gather of runs/test.py:133 runs on a side stream from a double-buffered copy of the step's probabilities, so that
+    # its launch latency overlaps the next replay instead of sitting between two replays (round 1: 14.27 -> 14.46 ms at 8 GPUs).
+    side = torch.cuda.Stream(dev) if world > 1 else None
+    stage = [torch.empty_like(eng.probs) for _ in range(2)] if world > 1 else None
+    staged_ev = [torch.cuda.Event() for _ in range(2)] if world > 1 else None
+    gather_ev = [torch.cuda.Event() for _ in range(2)] if world > 1 else None
+    counter = [0]
 
     def step():
         eng.graph.replay()
         if world > 1:
-            dist.all_gather_into_tensor(gathered, eng.probs)      # the logits gather of runs/test.py:133
+            i = counter[0] & 1
+            main = torch.cuda.current_stream()
+            if counter[0] >= 2:
+                main.wait_event(gather_ev[i])            # the gather that last read this staging buffer
+            stage[i].copy_(eng.probs, non_blocking=True)
+            staged_ev[i].record(main)
+            with torch.cuda.stream(side):
+                side.wait_event(staged_ev[i])
+                dist.all_gather_into_tensor(gathered, stage[i])
+                gather_ev[i].record(side)
+            counter[0] += 1
 
     for _ in range(args.warmup):
         step()
@@ -363,6 +415,8 @@ def main():
     e0.record()
     for _ in range(args.steps):
         step()
+    if world > 1:
+        torch.cuda.current_stream().wait_stream(side)      # the last gathers are part of the timed region
     e1.record()
     torch.cuda.synchronize()
     if world > 1:
@@ -376,7 +430,8 @@ def main():
 
     # ---- end to end through the public API, host buffers ----
     e2e = None
-    if not args.no_e2e:
+    e2e_u8 = None
+    if not args.no_e2e and not light:
         import dist_b200.models.base  # noqa: F401
         from dist_b200.config import Config
         from dist_b200.models.base.builder import build_model
@@ -475,8 +530,19 @@ def main():
                     "achieved": top_tf, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": top_tf / pk["tf_sustained"],
                     "traffic": traffic, "flop_per_launch": t["flops"] // max(t["launches"], 1), "us_per_launch": 1e3 * t["ms"] / max(t["launches"], 1),
                     "peak_source": pk["source"] + " sustained cuBLAS bf16 (kernel timed inside a long step); burst peak %.1f" % pk["tf_burst"]}
+        # HBM-bound side: the fused TemporalNet launches (algorithmic bytes: fp32 stream in, fp32 stream + bf16 copy out, bf16 i2t term in)
+        roofline_hbm = None
+        if "dist.tn" in by_name:
+            tn = by_name["dist.tn"]
+            gbs = tn["bytes"] / (tn["ms"] / 1e3) / 1e9
+            roofline_hbm = {"bound": "hbm", "kernel": "temporalnet_kernel @ dist.tn (%d launches per step)" % tn["launches"], "achieved": gbs,
+                            "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"], "bytes_per_launch": tn["bytes"] // max(tn["launches"], 1),
+                            "us_per_launch": 1e3 * tn["ms"] / max(tn["launches"], 1), "traffic": None,
+                            "note": "SIMT-issue / LSU bound, not HBM bound (DESIGN.md 4.7): the fraction is reported against the HBM roofline the north star names"}
         cpu = None
-        if not args.no_cpu_baseline:
+        if world > 1:
+            cpu = {"value": None, "unit": "clips/s", "cores": 0, "kind": "port", "sample": "skipped: measured at N=1 only (the other ranks would idle in a barrier)"}
+        elif not args.no_cpu_baseline and not light:
             heavy = arch.width >= 1024 or arch.frames > 16
             v, cores, sample = cpu_reference(arch, sd, 1 if heavy else 2, 1 if heavy else 3)
             cpu = {"value": v, "unit": "clips/s", "cores": cores, "kind": "port", "sample": sample}
@@ -491,16 +557,19 @@ def main():
                            sum(t.numel() * t.element_size() for t in vars(eng).values() if torch.is_tensor(t)) / 1e9),
                        "gflop_per_clip": round(fl["total"] / 1e9, 1), "weights": "random init (reference distributions), seed 0"},
             "model_tflops": value / world * fl["total"] / 1e12,
-            "roofline": roofline,
+            "roofline": roofline, "roofline_hbm": roofline_hbm,
             "gemm_all": {"launches": fam.get("gemm_vit", {}).get("launches", 0) + fam.get("gemm_dist", {}).get("launches", 0),
                          "achieved": achieved, "unit": "TFLOP/s", "frac": achieved / pk["tf_sustained"]},
             "cpu_baseline": cpu, "e2e": e2e, "e2e_uint8_frames": e2e_u8 if e2e is not None else None, "gpu_launches": eng.num_launches * args.steps, "launches_per_step": eng.num_launches,
             "kernels": kernels, "clocks": clocks,
         }
-        print(json.dumps(line))
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    else:
+        line = None
+    del eng, eng2
+    if e2e is not None:
+        del model, enc
+    torch.cuda.empty_cache()
+    return line
 
 
 if __name__ == "__main__":

@@ -73,7 +73,8 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) attention_simt_kernel(const T*
 
 template <typename T, bool CAUSAL>
 static void launch_variant(const void* qkv, void* out, unsigned grid, size_t smem, int tokens, int heads, cudaStream_t stream) {
-    static bool done = false;
+    static bool done_dev[DISTB200_MAX_DEVICES] = {};
+    bool& done = done_dev[current_device()];
     if (!done) { cudaFuncSetAttribute(attention_simt_kernel<T, CAUSAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); done = true; }
     DISTB200_LAUNCH((attention_simt_kernel<T, CAUSAL>), grid, ATT_WARPS * 32, smem, stream, (const T*)qkv, (T*)out, tokens, heads);
 }

@@ -449,7 +449,8 @@ int attention_tc_launch(const void* qkv, void* out, int frames, int tokens, int 
     args.items = (long long)frames * heads;
     DISTB200_REQUIRE(args.items * args.q_tiles < (1ll << 31), "attention(tcgen05): too many tiles");
     const int smem = Q_RING * (int)Q_TILE_BYTES + KV_STAGES * 2 * keys_ld * HD * 2 + 1024;
-    static int smem_set = 0;
+    static int smem_set_dev[DISTB200_MAX_DEVICES] = {};
+    int& smem_set = smem_set_dev[current_device()];
     if (smem > smem_set) {
         cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         DISTB200_REQUIRE(e == cudaSuccess, "attention(tcgen05): cannot reserve %d bytes of shared memory: %s", smem, cudaGetErrorString(e));

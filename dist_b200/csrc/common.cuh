@@ -97,15 +97,23 @@ inline void launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_
 #define DISTB200_LAUNCH(kernel, grid, block, smem, stream, ...) \
     ::distb200::launch_kernel(kernel, dim3(grid), dim3(block), (size_t)(smem), (cudaStream_t)(stream), __VA_ARGS__)
 
+// Per-DEVICE caches (a process may drive several GPUs: attributes set with cudaFuncSetAttribute and the SM count belong to the
+// current device, not to the process).
+constexpr int DISTB200_MAX_DEVICES = 64;
+inline int current_device() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return (dev >= 0 && dev < DISTB200_MAX_DEVICES) ? dev : 0;
+}
+
 inline int sm_count() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-        if (n <= 0) n = 148;
+    static int n[DISTB200_MAX_DEVICES] = {};
+    const int dev = current_device();
+    if (n[dev] == 0) {
+        cudaDeviceGetAttribute(&n[dev], cudaDevAttrMultiProcessorCount, dev);
+        if (n[dev] <= 0) n[dev] = 148;
     }
-    return n;
+    return n[dev];
 }
 
 // implemented in gemm_tcgen05.cu / gemm_simt.cu

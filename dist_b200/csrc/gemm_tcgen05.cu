@@ -717,7 +717,8 @@ int gemm_tcgen05_launch(const distb200_gemm_desc& d, cudaStream_t stream) {
     }
 
     const int smem = args.stages * (int)stage_bytes + staging_bytes(ew) + 1024 + 8 * (2 * MAX_STAGES + 4) + 16;
-    static bool attr_done = false;
+    static bool attr_done_dev[DISTB200_MAX_DEVICES] = {};
+    bool& attr_done = attr_done_dev[current_device()];
     if (!attr_done) {
         const void* fns[4] = {(const void*)gemm_tcgen05_kernel<1, 8>, (const void*)gemm_tcgen05_kernel<2, 8>,
                               (const void*)gemm_tcgen05_kernel<1, 12>, (const void*)gemm_tcgen05_kernel<2, 12>};

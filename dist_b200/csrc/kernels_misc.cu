@@ -510,6 +510,73 @@ __global__ void __launch_bounds__(1024) class_head_kernel(const float* __restric
     for (int c = tid; c < C; c += blockDim.x) probs[(long long)b * C + c] = __expf(sl[c] - mx) / den;
 }
 
+// class_head with the zero-shot / prediction-fusion branch of clip.py:519-527 fused in: the clip's video embedding and its t
+// per-frame CLIP image embeddings are scored against the label matrix in one pass; logits = w * video + (1 - w) * mean_t frame.
+// Also writes the L2-normalised frame embeddings (the `img_logits` the reference returns on this branch).
+__global__ void __launch_bounds__(1024) class_head_fused_kernel(const float* __restrict__ emb, const float* __restrict__ img, int t, float w,
+                                                               const float* __restrict__ text_n, float scale, int E, int C, float* logits,
+                                                               float* probs, float* img_n) {
+    grid_dep_sync();
+    extern __shared__ float sh[];          // [E] current vector, [C] blended logits, [32] scratch
+    float* se = sh;
+    float* sl = sh + E;
+    float* red = sl + C;
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+    for (int c = tid; c < C; c += blockDim.x) sl[c] = 0.f;
+    for (int f = -1; f < t; ++f) {
+        const float* src = f < 0 ? emb + (long long)b * E : img + ((long long)b * t + f) * E;
+        const float weight = f < 0 ? w : (1.0f - w) / (float)t;
+        __syncthreads();
+        float ss = 0.f;
+        for (int e = tid; e < E; e += blockDim.x) {
+            const float v = src[e];
+            se[e] = v;
+            ss += v * v;
+        }
+        ss = warp_sum(ss);
+        if (lane == 0) red[warp] = ss;
+        __syncthreads();
+        float tot = 0.f;
+        for (int i = 0; i < nw; ++i) tot += red[i];
+        const float rn = rsqrtf(tot);
+        if (f >= 0 && img_n)
+            for (int e = tid; e < E; e += blockDim.x) img_n[((long long)b * t + f) * E + e] = se[e] * rn;
+        const float inv = scale * rn * weight;
+        for (int c = warp; c < C; c += nw) {
+            const float* tr = text_n + (long long)c * E;
+            float d0 = 0.f, d1 = 0.f;
+            int e = lane;
+            for (; e + 32 < E; e += 64) {
+                const float t0 = __ldg(tr + e), t1 = __ldg(tr + e + 32);
+                d0 = fmaf(se[e], t0, d0); d1 = fmaf(se[e + 32], t1, d1);
+            }
+            for (; e < E; e += 32) d0 = fmaf(se[e], __ldg(tr + e), d0);
+            const float dot = warp_sum(d0 + d1);
+            if (lane == 0) sl[c] += dot * inv;           // class c belongs to this warp in every round: no race
+        }
+    }
+    __syncthreads();
+    if (logits)
+        for (int c = tid; c < C; c += blockDim.x) logits[(long long)b * C + c] = sl[c];
+    if (!probs) return;
+    float mx = -INFINITY;
+    for (int c = tid; c < C; c += blockDim.x) mx = fmaxf(mx, sl[c]);
+    mx = warp_max(mx);
+    if (lane == 0) red[warp] = mx;
+    __syncthreads();
+    mx = red[0];
+    for (int i = 1; i < nw; ++i) mx = fmaxf(mx, red[i]);
+    __syncthreads();
+    float den = 0.f;
+    for (int c = tid; c < C; c += blockDim.x) den += __expf(sl[c] - mx);
+    den = warp_sum(den);
+    if (lane == 0) red[warp] = den;
+    __syncthreads();
+    den = 0.f;
+    for (int i = 0; i < nw; ++i) den += red[i];
+    for (int c = tid; c < C; c += blockDim.x) probs[(long long)b * C + c] = __expf(sl[c] - mx) / den;
+}
+
 
 // ---------------------------------------------------------------------------------------------------
 // multi-view ensemble (utils/meters.py:83-115): every clip adds (or max-es) its class scores into the row of its video
@@ -811,6 +878,18 @@ extern "C" int distb200_class_head(const float* emb, const float* text_n, float 
     DISTB200_REQUIRE(smem <= 48 * 1024, "class_head: E + C too large for one block (%zu bytes)", smem);
     DISTB200_LAUNCH(class_head_kernel, batch, 1024, smem, (cudaStream_t)stream, emb, text_n, scale, embed_dim, classes, logits, probs);
     return check_launch("class_head");
+}
+
+extern "C" int distb200_class_head_fused(const float* emb, const float* img, int32_t frames_per_clip, float w, const float* text_n, float scale,
+                                         int32_t batch, int32_t embed_dim, int32_t classes, float* logits, float* probs, float* img_n,
+                                         void* stream) {
+    if (batch == 0) return 0;
+    DISTB200_REQUIRE(emb && img && text_n && frames_per_clip >= 1, "class_head_fused: null pointer / no frames");
+    const size_t smem = (size_t)(embed_dim + classes + 32) * sizeof(float);
+    DISTB200_REQUIRE(smem <= 48 * 1024, "class_head_fused: E + C too large for one block (%zu bytes)", smem);
+    DISTB200_LAUNCH(class_head_fused_kernel, batch, 1024, smem, (cudaStream_t)stream, emb, img, frames_per_clip, w, text_n, scale, embed_dim, classes,
+                    logits, probs, img_n);
+    return check_launch("class_head_fused");
 }
 
 extern "C" int distb200_embed_tokens(const int64_t* ids, const float* table, const float* pos, int64_t seqs, int32_t ctx, int32_t width,

@@ -629,10 +629,9 @@ __global__ void __launch_bounds__(TN_THREADS, 1) temporalnet_kernel(const __grid
 
 template <int C, bool HAS_U>
 int launch_instance(const TnArgs& args, int grid, int smem, cudaStream_t stream) {
-    static bool attr_done[64] = {};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev >= 0 && dev < 64 && !attr_done[dev]) {
+    static bool attr_done[DISTB200_MAX_DEVICES] = {};
+    const int dev = current_device();
+    if (!attr_done[dev]) {
         cudaError_t e = cudaFuncSetAttribute(temporalnet_kernel<C, HAS_U>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         DISTB200_REQUIRE(e == cudaSuccess, "temporalnet: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
         attr_done[dev] = true;

@@ -311,7 +311,8 @@ int wgrad_tcgen05_launch(const distb200_wgrad_desc& d, cudaStream_t stream) {
         if (make_map(&args.tm_dy, base, 3, dims, str, box, "wgrad dY")) return 1;
     }
     const int smem = W_STAGES * (int)W_STAGE_BYTES + 1024;
-    static bool attr_done = false;
+    static bool attr_done_dev[DISTB200_MAX_DEVICES] = {};
+    bool& attr_done = attr_done_dev[current_device()];
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(wgrad_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         DISTB200_REQUIRE(e == cudaSuccess, "gemm_wgrad(tcgen05): cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));

@@ -117,6 +117,9 @@ class PackedWeights:
         self.pos = f32(pos)                                                                    # [N, D]
         self.cls_row = f32((sd["visual.class_embedding"].float() + pos[0]).reshape(1, D))      # clip.py:274-275
         self.ln_pre = (f32(sd["visual.ln_pre.weight"]), f32(sd["visual.ln_pre.bias"]))
+        # per-frame CLIP image embeddings (clip.py:291-298): only the zero-shot / prediction-fusion branch and `img_logits` read them
+        self.vis_ln_post = (f32(sd["visual.ln_post.weight"]), f32(sd["visual.ln_post.bias"])) if "visual.ln_post.weight" in sd else None
+        self.vis_proj_w = op(sd["visual.proj"].float().t()) if "visual.proj" in sd else None          # [E, D]
         self.vit = []
 
         def folded(w_key, b_key, g_key, beta_key):
@@ -256,10 +259,15 @@ class DistEngine:
     CLIP_STD = (0.26862954, 0.26130258, 0.27577711)
 
     def __init__(self, state_dict, arch: DistArch, batch, device="cuda", precision="bf16", text_features=None,
-                 gemm_impl=ops.IMPL_AUTO, attn_impl=ops.IMPL_AUTO, input_format="float", mean=None, std=None):
-        """``input_format="uint8"``: clips arrive as decoded frames ``[b, T, H, W, 3]`` uint8 and ToTensorVideo +
+                 gemm_impl=ops.IMPL_AUTO, attn_impl=ops.IMPL_AUTO, input_format="float", mean=None, std=None, image_logits=None,
+                 fusion_weight=0.5):
+        """``image_logits``: ``None`` (DiST's own path: the ViT's ``ln_post`` / ``proj`` are dead code, clip.py:291-298), ``"raw"`` (also
+        compute the per-frame CLIP image embeddings ``img_emb`` [b*t, E]) or ``"fused"`` (the zero-shot / prediction-fusion branch of
+        clip.py:519-527: class scores = ``fusion_weight`` x video logits + the rest x mean per-frame logits; ``img_emb_n`` holds the
+        normalised embeddings).  ``input_format="uint8"``: clips arrive as decoded frames ``[b, T, H, W, 3]`` uint8 and ToTensorVideo +
         NormalizeVideo (``dataset/base/ssv2.py:137-143``) are fused into the patch-row kernel."""
-        assert precision in ("bf16", "fp32") and input_format in ("float", "uint8")
+        assert precision in ("bf16", "fp32") and input_format in ("float", "uint8") and image_logits in (None, "raw", "fused")
+        self.image_logits, self.fusion_weight = image_logits, float(fusion_weight)
         self.input_format = input_format
         self.mean, self.std = tuple(mean or self.CLIP_MEAN), tuple(std or self.CLIP_STD)
         arch.validate()
@@ -280,9 +288,13 @@ class DistEngine:
     def set_text_features(self, feats):
         """Cached label embeddings [C, E] (clip.py:437-452); normalised once (clip.py:514)."""
         f = feats.detach().to(device=self.device, dtype=torch.float32)
-        self.text_n = (f / f.norm(dim=1, keepdim=True)).contiguous()
-        if hasattr(self, "logits") and self.text_n.shape[0] != self.logits.shape[1]:
+        f = (f / f.norm(dim=1, keepdim=True)).contiguous()
+        if hasattr(self, "logits") and f.shape[0] != self.logits.shape[1]:
             raise ValueError("text features changed the number of classes; rebuild the engine")
+        if getattr(self, "text_n", None) is not None and self.text_n.shape == f.shape:
+            self.text_n.copy_(f)            # in place: the planned head call (and a captured graph) keep pointing at this buffer
+        else:
+            self.text_n = f
 
     def _alloc(self):
         a, b, dev, adt = self.arch, self.batch, self.device, self.adt
@@ -369,6 +381,10 @@ class DistEngine:
         C = self.text_n.shape[0] if self.text_n is not None else max(a.num_classes, 1)
         self.logits = z(b, C, dtype=f32)
         self.probs = z(b, C, dtype=f32)
+        if self.image_logits:
+            self.img_ln = z(F, D)
+            self.img_emb = z(F, a.embed_dim, dtype=f32)
+            self.img_emb_n = z(F, a.embed_dim, dtype=f32)
 
     # ------------------------------------------------------------------------------------------
     def _gemm(self, *args, **kw):
@@ -651,11 +667,20 @@ class DistEngine:
         self._lin(self.clsmean, w.pcls_w, w.pcls_b, self.zbuf, res=self.top, name="tail.proj_spatial_cls")
         self._ln(self.zbuf, w.ln_post, self.z_ln, name="tail.ln_post")
         self._lin(self.z_ln, w.proj_w, None, self.emb, name="tail.proj")
+        if self.image_logits:
+            # ln_post of the last block's class token, times visual.proj (clip.py:291-298): rows N*D apart in the residual stream
+            assert w.vis_ln_post is not None and w.vis_proj_w is not None, "the checkpoint has no visual.ln_post / visual.proj"
+            add(ops.layernorm(self.h, w.vis_ln_post[0], w.vis_ln_post[1], self.img_ln, rows=F, cols=a.width, ld_in1=N * a.width, name="head.img.ln_post"))
+            self._lin(self.img_ln, w.vis_proj_w, None, self.img_emb, name="head.img.proj")
         self.head_call = None
         if self.text_n is not None:
-            # clip.py:511-518 + base_blocks.py:579-585
-            self.head_call = ops.class_head(self.emb, self.text_n, w.logit_scale, b, a.embed_dim, self.text_n.shape[0],
-                                            self.logits, self.probs, name="head.class_scores")
+            # clip.py:511-518 + base_blocks.py:579-585 (+ clip.py:519-527 on the zero-shot branch)
+            if self.image_logits == "fused":
+                self.head_call = ops.class_head_fused(self.emb, self.img_emb, t, self.fusion_weight, self.text_n, w.logit_scale, b, a.embed_dim,
+                                                      self.text_n.shape[0], self.logits, self.probs, img_n=self.img_emb_n, name="head.class_scores")
+            else:
+                self.head_call = ops.class_head(self.emb, self.text_n, w.logit_scale, b, a.embed_dim, self.text_n.shape[0],
+                                                self.logits, self.probs, name="head.class_scores")
             add(self.head_call)
 
     # ------------------------------------------------------------------------------------------

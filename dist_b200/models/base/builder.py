@@ -23,13 +23,11 @@ def build_model(cfg, gpu_id=None):
     if cfg.MODEL.EMA.ENABLE:
         raise NotImplementedError("MODEL.EMA is outside the DiST forward path (ModelEmaV2 is undefined in the reference as well, builder.py:13,57)")
 
-    if cfg.NUM_GPUS * cfg.NUM_SHARDS > 1 and torch.distributed.is_available() and torch.distributed.is_initialized():
-        # The reference wraps the whole model in DDP with find_unused_parameters=True (builder.py:69-74), which
-        # all-reduces the frozen CLIP parameters as zero buckets.  Here only dist_net parameters are trainable
-        # (the rest are frozen by flag), so DDP reduces exactly the 19-40 M trainable values.
-        for name, p in model.named_parameters():
-            if ".dist_net." not in name:
-                p.requires_grad_(False)
-        if any(p.requires_grad for p in model.parameters()):
-            model = torch.nn.parallel.DistributedDataParallel(module=model, device_ids=[cur_device], output_device=cur_device)
+    # The reference wraps the model in DistributedDataParallel here (builder.py:69-74) because it trains through autograd.  On this
+    # path the nn.Module owns parameters only: its forward runs the planned CUDA inference engine (no autograd graph), and
+    # fine-tuning is dist_b200.runs.train.Trainer - planned forward + backward + ONE flat NCCL all-reduce of the dist_net
+    # gradients + fused AdamW.  A DDP wrapper would advertise a backward that does not exist, so none is applied; only the
+    # trainable set is marked like the reference's optimiser sees it (optimizer.py:148: tensors named dist_net).
+    for name, p in model.named_parameters():
+        p.requires_grad_(".dist_net." in name)
     return model, model_ema

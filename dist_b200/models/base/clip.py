@@ -228,6 +228,10 @@ class CLIP(nn.Module):
         self.precision = getattr(b200, "PRECISION", "bf16") if b200 is not None else "bf16"
         self.use_graph = bool(getattr(b200, "CUDA_GRAPH", True)) if b200 is not None else True
         self.text_features = None
+        test_cfg = getattr(cfg, "TEST", None)
+        zs = getattr(test_cfg, "ZEROSHOT", None) if test_cfg is not None else None
+        self.zero_shot_test = bool(getattr(zs, "ENABLE", False)) if zs is not None else False              # clip.py:327
+        self.want_img_logits = bool(getattr(b200, "IMG_LOGITS", False)) if b200 is not None else False
         self._engines = {}
 
     # ---- label embeddings ---------------------------------------------------------------------
@@ -261,9 +265,11 @@ class CLIP(nn.Module):
         """``CLIP.cache_text`` (``clip.py:436-452``): the label set is encoded once and reused while its size is unchanged."""
         if others is not None and "label_embeddings" in others:            # clip.py:437-439
             return others["label_embeddings"], None, others
-        if self._text_cache is None or self._text_cache[0].shape[0] != text.shape[0]:
+        names = ("transformer.", "token_embedding.", "positional_embedding", "ln_final.", "text_projection")
+        version = sum(p._version for n, p in self.named_parameters() if n.startswith(names))     # a load_state_dict after the first call invalidates
+        if self._text_cache is None or self._text_cache[0].shape[0] != text.shape[0] or self._text_cache[2] != version:
             feats, eot, others = self.encode_text(text, others)
-            self._text_cache = (feats, eot)
+            self._text_cache = (feats, eot, version)
         return self._text_cache[0], self._text_cache[1], others
 
     def _text_from(self, text, others):
@@ -282,17 +288,32 @@ class CLIP(nn.Module):
             "embeddings are cached - call set_text_features([C, E]) with embeddings computed once")
 
     # ---- engine cache -------------------------------------------------------------------------
+    def _image_logits_mode(self):
+        """``"fused"`` on the zero-shot test branch (``TEST.ZEROSHOT.ENABLE`` in eval, clip.py:327,519), ``"raw"`` when the config asks
+        for the per-frame CLIP embeddings (``B200.IMG_LOGITS``), else ``None``: DiST never reads them (clip.py:291-298 is dead code on
+        its path), so they are not computed unless wanted."""
+        if self.zero_shot_test and not self.training:
+            return "fused"
+        return "raw" if self.want_img_logits else None
+
     def _engine(self, batch, device, text, input_format="float"):
         from ...engine import DistEngine
         version = sum(p._version for p in self.parameters())
         tkey = None if text is None else (text.data_ptr(), tuple(text.shape), text._version)
-        key = (batch, str(device), self.precision, input_format)
+        mode = self._image_logits_mode() if text is not None else None
+        key = (batch, str(device), self.precision, input_format, mode)
         hit = self._engines.get(key)
         if hit is not None and hit[1] == version and hit[2] == tkey:
             return hit[0]
+        if hit is not None and hit[1] == version and text is not None and hit[0].text_n is not None and hit[0].text_n.shape == text.shape:
+            # only the label matrix changed (FREEZE_TEXT false, or fresh others["label_embeddings"] per call): refresh it in place
+            # instead of re-packing every weight and re-capturing the graph
+            hit[0].set_text_features(text)
+            self._engines[key] = (hit[0], version, tkey)
+            return hit[0]
         sd = {k: v for k, v in self.state_dict().items()}
         eng = DistEngine(sd, self.arch, batch, device=device, precision=self.precision, text_features=text, input_format=input_format,
-                         mean=getattr(self.cfg.DATA, "MEAN", None), std=getattr(self.cfg.DATA, "STD", None))
+                         mean=getattr(self.cfg.DATA, "MEAN", None), std=getattr(self.cfg.DATA, "STD", None), image_logits=mode)
         if self.use_graph:
             eng.capture()
         self._engines[key] = (eng, version, tkey)
@@ -303,6 +324,11 @@ class CLIP(nn.Module):
 
     # ---- forwards (clip.py:460-533) -------------------------------------------------------------
     def forward(self, image, text, others=None):
+        if self.training and torch.is_grad_enabled():
+            raise RuntimeError(
+                "dist_b200: this module's forward is the planned CUDA inference path and builds no autograd graph, so "
+                "loss.backward() cannot train it.  Fine-tune with dist_b200.runs.train.Trainer (planned forward + backward + "
+                "all-reduce + AdamW, runs/train.py:97-112 of the reference), or call model.eval() / torch.no_grad() for inference.")
         if text is not None or (others is not None and "label_embeddings" in others):
             return self.forward_with_text(image, text, others)
         return self.forward_without_text(image)
@@ -343,12 +369,26 @@ class CLIP(nn.Module):
         emb = eng.forward(clips if u8 else clips.float(), use_graph=self.use_graph)
         logits = eng.logits.clone()
         vid = emb / emb.norm(dim=1, keepdim=True)                           # clip.py:513 (returned, not on the scored path)
+        # img_logits: the per-frame CLIP embeddings ln_post(cls) @ proj [B*t, E] - L2-normalised on the fusion branch, raw otherwise
+        # (clip.py:520,532) - or None when nothing asked for them (see _image_logits_mode)
+        img = None
+        if eng.image_logits == "fused":
+            img = eng.img_emb_n.clone()
+        elif eng.image_logits == "raw":
+            img = eng.img_emb.clone()
         return {"logits_per_image": logits, "logits_per_text": logits.t(), "probs_per_image": eng.probs.clone(),
-                "img_logits": None, "vid_logits": vid[:, None, :]}
+                "img_logits": img, "vid_logits": vid[:, None, :]}
 
 
 def build_model(cfg, state_dict):
-    """Infer the geometry from the checkpoint like ``clip.py:564-611`` and load it (``strict=False``)."""
+    """Infer the geometry from the checkpoint like ``clip.py:564-611`` and load it with ``load_state_dict(strict=False)``
+    semantics: missing and unexpected keys are tolerated (and recorded on the model), a key whose SHAPE differs raises - e.g. a
+    ``cls_token`` / ``positional_embedding`` trained for another frame count (the weights are frame-count specific).
+
+    ``dist_net`` tensors absent from the checkpoint - the normal case when fine-tuning starts from an OpenAI CLIP archive - get the
+    reference's own initialisation (``dist.py:77-79,120-121,195-220``: truncated normal, std 0.02, for every Linear / Conv weight and
+    token, zero biases, LayerNorm at identity), not torch's module defaults."""
+    import logging
     from ...text import has_text_tower, text_geometry
     arch = arch_from_cfg(cfg, state_dict)
     tk = {}
@@ -358,10 +398,28 @@ def build_model(cfg, state_dict):
                   transformer_layers=g["layers"])
     model = CLIP(cfg, arch.embed_dim, arch.resolution, arch.layers, arch.width, arch.patch, arch=arch, **tk)
     own = model.state_dict()
-    usable = {k: v for k, v in state_dict.items() if k in own and own[k].shape == v.shape}
+    bad = ["%s: checkpoint %s vs model %s" % (k, tuple(v.shape), tuple(own[k].shape)) for k, v in state_dict.items()
+           if k in own and torch.is_tensor(v) and tuple(own[k].shape) != tuple(v.shape)]
+    if bad:
+        raise RuntimeError("size mismatch for %d tensor(s) while loading the checkpoint (weights are frame-count / geometry specific):\n  %s"
+                           % (len(bad), "\n  ".join(bad[:20])))
+    usable = {k: v for k, v in state_dict.items() if k in own}
     missing = sorted(set(own) - set(usable))
+    unexpected = sorted(k for k in state_dict if k not in own)
+    fresh = [k for k in missing if k.startswith("dist_net.")]
+    if fresh:
+        seed = int(getattr(cfg, "RANDOM_SEED", 0))
+        init = synth.synth_state_dict(arch, seed=seed, init="reference")
+        usable.update({k: init[k] for k in fresh})
     model.load_state_dict(usable, strict=False)
-    model.missing_keys = missing
+    model.missing_keys, model.unexpected_keys, model.initialised_keys = missing, unexpected, fresh
+    log = logging.getLogger(__name__)
+    if fresh:
+        log.info("dist_net: %d tensor(s) not in the checkpoint were initialised like the reference (trunc_normal 0.02 / zero bias)", len(fresh))
+    if [k for k in missing if k not in fresh]:
+        log.warning("missing keys (kept at module defaults): %s", [k for k in missing if k not in fresh][:20])
+    if unexpected:
+        log.info("unexpected checkpoint keys ignored: %d (e.g. %s)", len(unexpected), unexpected[:5])
     return model.eval()
 
 

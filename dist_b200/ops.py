@@ -93,6 +93,14 @@ def lib():
                 raise RuntimeError(
                     "dist_b200: the CUDA extension {} is missing and could not be built ({}). There is no "
                     "CPU or PyTorch fallback for this path.".format(path, exc)) from exc
+            # a prebuilt library exists but is OLDER than the sources and the rebuild failed: running it would silently test stale
+            # kernels.  Refuse unless explicitly allowed (a GPU box without nvcc that received a library built elsewhere in time).
+            if os.environ.get("DISTB200_ALLOW_STALE", "0") != "1":
+                raise RuntimeError(
+                    "dist_b200: {} is older than its sources and rebuilding failed ({}). Rebuild with `python -m dist_b200.build` "
+                    "or set DISTB200_ALLOW_STALE=1 to load the stale library knowingly.".format(path, str(exc)[:300])) from exc
+            import warnings
+            warnings.warn("dist_b200: loading a STALE {} (rebuild failed: {})".format(path, str(exc)[:200]))
     try:
         L = C.CDLL(path)
     except OSError as exc:
@@ -118,6 +126,7 @@ def lib():
     L.distb200_rows_bcast.argtypes = [vp, i64, i64, i32, vp, i64, i32, vp, i64, vp]
     L.distb200_mean_rows.argtypes = [vp, i64, i32, i64, i32, vp, i32, vp]
     L.distb200_class_head.argtypes = [vp, vp, f32, i32, i32, i32, vp, vp, vp]
+    L.distb200_class_head_fused.argtypes = [vp, vp, i32, f32, vp, f32, i32, i32, i32, vp, vp, vp, vp]
     # fine-tuning step
     L.distb200_gemm_wgrad.argtypes = [C.POINTER(WgradDesc), vp]
     L.distb200_quickgelu.argtypes = [vp, i32, vp, vp, i32, i64, vp]
@@ -134,7 +143,7 @@ def lib():
     for name in TRAIN_EXPORTS:
         getattr(L, name).restype = C.c_int
     for name in ("row_stats", "gemm", "layernorm", "attention", "cross_attention", "patchify", "patchify_u8", "rows_bcast", "mean_rows", "class_head", "view_ensemble",
-                 "topk_correct", "attention_causal", "embed_tokens", "gather_eot", "row_stats_finalize", "temporalnet"):
+                 "topk_correct", "attention_causal", "embed_tokens", "gather_eot", "row_stats_finalize", "temporalnet", "class_head_fused"):
         getattr(L, "distb200_" + name).restype = C.c_int
     assert L.distb200_version() == 100 and L.distb200_arch() == 100
     _LIB = L
@@ -148,7 +157,7 @@ TRAIN_EXPORTS = ("distb200_gemm_wgrad", "distb200_quickgelu", "distb200_quickgel
 EXPORTS = TRAIN_EXPORTS + ("distb200_version", "distb200_arch", "distb200_last_error", "distb200_gemm", "distb200_row_stats", "distb200_layernorm",
            "distb200_attention", "distb200_cross_attention", "distb200_patchify", "distb200_patchify_u8", "distb200_view_ensemble", "distb200_topk_correct", "distb200_rows_bcast",
            "distb200_mean_rows", "distb200_class_head", "distb200_attention_causal", "distb200_embed_tokens", "distb200_gather_eot",
-           "distb200_row_stats_finalize", "distb200_temporalnet")
+           "distb200_row_stats_finalize", "distb200_temporalnet", "distb200_class_head_fused")
 
 
 class DistB200Error(RuntimeError):
@@ -397,6 +406,14 @@ def mean_rows(src, row_stride, count, batch, cols, out, name="mean_rows"):
 def class_head(emb, text_n, scale, batch, embed_dim, classes, logits, probs, name="class_head"):
     args = (emb.data_ptr(), text_n.data_ptr(), float(scale), int(batch), int(embed_dim), int(classes), _ptr(logits), _ptr(probs))
     return Call(lib().distb200_class_head, args, name, keep=(emb, text_n, logits, probs))
+
+
+def class_head_fused(emb, img, frames_per_clip, w, text_n, scale, batch, embed_dim, classes, logits, probs, img_n=None, name="class_head_fused"):
+    """Class scores with the zero-shot / prediction-fusion average of clip.py:519-527 (video logits and mean per-frame CLIP logits)."""
+    assert emb.dtype == img.dtype == text_n.dtype == torch.float32
+    args = (emb.data_ptr(), img.data_ptr(), int(frames_per_clip), float(w), text_n.data_ptr(), float(scale), int(batch), int(embed_dim), int(classes),
+            _ptr(logits), _ptr(probs), _ptr(img_n))
+    return Call(lib().distb200_class_head_fused, args, name, keep=(emb, img, text_n, logits, probs, img_n))
 
 
 # ---- fine-tuning step ------------------------------------------------------------------------------

@@ -93,16 +93,15 @@ class ParamTable:
                 packed[k], self.unpack[k] = w, (lambda p, shp=tuple(w.shape): p.reshape(shp))
             packed[k] = packed[k].contiguous()
 
-        def decay_of(k):                                            # optimizer.py:150-166
-            if k.endswith("cls_token") or k.endswith("positional_embedding"):
-                return 0.0
-            if "bias" in k or sd[k].dim() == 1:
-                return 0.0
-            return weight_decay
+        from .models.utils.optimizer import weight_decay_of
+
+        def decay_of(k):                                            # the group rule of optimizer.py:150-166
+            return weight_decay_of(k, sd[k].dim(), weight_decay)
 
         used = [k for k in names if k not in self.unused]
-        decayed = [k for k in used if decay_of(k) > 0]
-        plain = [k for k in used if decay_of(k) == 0]
+        from .models.utils.optimizer import decay_class
+        decayed = [k for k in used if decay_class(k, sd[k].dim()) == "normal"]
+        plain = [k for k in used if decay_class(k, sd[k].dim()) != "normal"]
         order = decayed + plain + list(self.unused)
         self.offset, off = {}, 0
         for group, attr in ((decayed, "n_decay"), (plain, "n_used"), (self.unused, "total")):

@@ -79,3 +79,30 @@ def load_state_dict(path):
 def save_checkpoint(path, state_dict, prefix=PREFIX):
     """``{"model_state": ...}`` with the ``BaseVideoModel`` prefix, as ``utils/checkpoint.py:329`` writes it."""
     torch.save({"model_state": collections.OrderedDict((prefix + k, v.detach().cpu()) for k, v in state_dict.items())}, path)
+
+
+def load_test_checkpoint(cfg, model, path=None):
+    """``utils/checkpoint.py:452-529`` (``load_test_checkpoint``) for this path: read ``TEST.CHECKPOINT_FILE_PATH`` (or ``path``),
+    strip the ``backbone.base_encoder.`` prefix the released DiST checkpoints carry and load the tensors into the model's CLIP
+    module.  Fails loudly when the checkpoint does not provide the DiST branches (a silent ``strict=False`` load of a checkpoint
+    whose keys all miss - e.g. prefixed keys into the un-prefixed module - would leave ``dist_net`` at its initial values).
+    Returns ``(missing_keys, unexpected_keys)``."""
+    path = path or getattr(cfg.TEST, "CHECKPOINT_FILE_PATH", "")
+    if not path:
+        raise ValueError("TEST.CHECKPOINT_FILE_PATH is empty and no path was given")
+    sd = load_state_dict(path)
+    m = model.module if hasattr(model, "module") else model
+    core = m.backbone.base_encoder if hasattr(m, "backbone") else m
+    own = core.state_dict()
+    bad = [k for k, v in sd.items() if k in own and tuple(own[k].shape) != tuple(v.shape)]
+    if bad:
+        raise RuntimeError("size mismatch for: %s (DiST weights are frame-count specific: cls_token / positional_embedding)" % bad[:10])
+    hit = [k for k in sd if k in own and k.startswith("dist_net.")]
+    want = [k for k in own if k.startswith("dist_net.")]
+    if len(hit) != len(want):
+        raise RuntimeError("the checkpoint provides %d of the %d dist_net tensors (first missing: %s)"
+                           % (len(hit), len(want), sorted(set(want) - set(hit))[:5]))
+    res = core.load_state_dict({k: v for k, v in sd.items() if k in own}, strict=False)
+    if hasattr(core, "refresh_engine"):
+        core.refresh_engine()
+    return list(res.missing_keys), sorted(k for k in sd if k not in own)

@@ -256,6 +256,15 @@ int distb200_mean_rows(const float* src, int64_t row_stride, int32_t count, int6
 int distb200_class_head(const float* emb, const float* text_n, float scale, int32_t batch, int32_t embed_dim,
                         int32_t classes, float* logits, float* probs, void* stream);
 
+/* The same head with the zero-shot / prediction-fusion branch (clip.py:519-527, TEST.ZEROSHOT.ENABLE) fused in: img
+ * [batch * frames_per_clip, embed_dim] are the per-frame CLIP image embeddings ln_post(class token) @ visual.proj (clip.py:291-298),
+ *     logits[b] = w * scale * cos(emb[b], text) + (1 - w) * mean_f scale * cos(img[b, f], text)
+ * (w = 0.5 in the reference unless its gating parameter is enabled), probs = softmax(logits).  img_n (optional) receives the
+ * L2-normalised image embeddings, which is what the reference returns as img_logits on this branch (clip.py:520,532). */
+int distb200_class_head_fused(const float* emb, const float* img, int32_t frames_per_clip, float w, const float* text_n, float scale,
+                              int32_t batch, int32_t embed_dim, int32_t classes, float* logits, float* probs, float* img_n,
+                              void* stream);
+
 
 /* Multi-view test ensemble on the device (TestMeter.update_stats, utils/meters.py:83-115, without the per-clip Python loop
  * and the .cpu() synchronisation of runs/test.py:136-145): for every clip i, video = clip_ids[i] / num_clips;

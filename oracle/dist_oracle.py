@@ -263,6 +263,23 @@ def class_scores(sd, emb, text_features, softmax=True):
     return torch.softmax(logits, dim=-1) if softmax else logits
 
 
+def image_embeddings(sd, last_tap):
+    """Per-frame CLIP image embeddings (``VisionTransformer.forward``, clip.py:291-298): ``ln_post`` of the class token of the LAST
+    ViT block, times ``visual.proj``.  last_tap [b*t, N, D] -> [b*t, E].  Returned as ``img_logits`` by ``CLIP.forward``
+    (clip.py:532); DiST itself does not use them, the zero-shot / prediction-fusion branch does."""
+    x = _ln(last_tap[:, 0], sd["visual.ln_post.weight"], sd["visual.ln_post.bias"])
+    return x @ sd["visual.proj"]
+
+
+def fused_class_scores(sd, emb, img, text_features, t, w=0.5):
+    """Zero-shot / prediction fusion (clip.py:519-527): ``w`` x the video logits + ``(1 - w)`` x the mean over a clip's t sparse
+    frames of the per-frame CLIP logits; both cosine logits share ``exp(logit_scale)``.  ``w`` = 0.5 unless the (never defined)
+    gating parameter is enabled.  emb [b, E], img [b*t, E] -> logits [b, C]."""
+    vid = class_scores(sd, emb, text_features, softmax=False)
+    fr = class_scores(sd, img, text_features, softmax=False)
+    return vid * w + fr.reshape(emb.shape[0], t, -1).mean(dim=1) * (1.0 - w)
+
+
 def encode_text(sd, ids):
     """CLIP text tower (``CLIP.encode_text``, clip.py:419-434; blocks = ``ResidualAttentionBlock``, clip.py:112-136, with the
     causal additive mask of clip.py:404-410).  ids int64 [C, ctx] -> (features [C, E], eot rows [C, W])."""

@@ -16,7 +16,10 @@ def inputs_for(fix):
 def check_inputs(fix, sd, clips, text, rtol=1e-6):
     """The seeded generators must reproduce the tensors the reference was run on."""
     def close(a, b):
-        return all(abs(x - y) <= rtol * max(1.0, abs(y)) for x, y in zip(a, b))
+        # [sum, sum of magnitudes]: the signed sum of a zero-mean tensor cancels to ~0, so both entries are compared on the scale of the
+        # magnitude sum (the generators normalise with reductions whose summation order depends on the host's thread count: 1e-8 relative)
+        scale = max(1.0, abs(b[1]))
+        return all(abs(x - y) <= rtol * scale for x, y in zip(a, b))
     assert close(synth.checksum({k: v for k, v in sd.items() if k != "logit_scale"}), fix["weights_checksum"]), "synthetic weights differ from the fixture's"
     assert close(synth.checksum(clips), fix["clips_checksum"]), "synthetic clips differ from the fixture's"
     assert close(synth.checksum(text), fix["text_checksum"]), "synthetic label embeddings differ from the fixture's"
