@@ -17,6 +17,8 @@
                    shipped constructor raises on a slicing typo after filling them).
   train_b16_16x32  BASELINE configs[4] at full size, one clip: loss, logits and the reference autograd's gradients of a dozen
                    ``dist_net`` tensors (sub-sampled) incl. ``temporal_nets.*.c_fc2``, ``integration_nets.*.ffn``, ``adapooling_nets.*.attn``.
+  tokenizer        ``dataset/utils/simple_tokenizer.py:64-179`` on prompts with punctuation, contractions, digits, HTML entities, accents,
+                   CJK and an over-long prompt (truncate=True): the ``[n, 77]`` id rows and the decoded strings.
   cpu_speed        wall time of the reference's own modules and of the oracle port for one B/16 8+16f clip on this container's
                    cores (how the ``--impl reference`` arm of bench.py, which can only run the port, relates to the real modules).
 """
@@ -265,13 +267,39 @@ def run_cpu_speed():
     print("[cpu_speed]", out)
 
 
+PROMPTS = [
+    "a video of a person pushing something from left to right", "Pretending to put something behind something", "a photo of a dog.",
+    "riding a mountain bike", "person's hands can't be seen; it's 3 o'clock!", "tai chi", "playing   ukulele\t(close-up)", "UPPER lower MiXeD",
+    "na\u00efve caf\u00e9 \u2014 d\u00e9j\u00e0 vu", "\u4eba\u5728\u8dd1\u6b65", "100% of 42 cats & dogs", "rock &amp; roll &lt;live&gt;", "hello<|endoftext|>world",
+    "supercalifragilisticexpialidocious antidisestablishmentarianism", "", "emoji \U0001f600 test", "e=mc^2 ... ok?!", "don't you'll we've I'm he'd she's they're",
+]
+
+
+def run_tokenizer():
+    """``dataset/utils/simple_tokenizer.py`` with its own merge list.  ``ftfy`` is not installed in this image; for these well-formed
+    prompts ``ftfy.fix_text`` is the identity, which is what the shim supplies."""
+    mod = types.ModuleType("ftfy")
+    mod.fix_text = lambda t: t
+    sys.modules.setdefault("ftfy", mod)
+    from dataset.utils import simple_tokenizer as st
+    tok = st.tokenize(PROMPTS, context_length=77)
+    long_prompt = " ".join(["very long prompt about something"] * 30)
+    trunc = st.tokenize([long_prompt], context_length=77, truncate=True)
+    out = {"prompts": PROMPTS, "ids": tok.tolist(), "long_prompt": long_prompt, "long_truncated": trunc.tolist(),
+           "decoded": [st._tokenizer.decode([t for t in row if t != 0]) for row in tok.tolist()],
+           "vocab_size": len(st._tokenizer.encoder), "bpe_file": "dataset/utils/bpe_simple_vocab_16e6.txt.gz"}
+    with open(os.path.join(GOLDEN, "tokenizer.json"), "w") as f:
+        json.dump(out, f)
+    print("[tokenizer] %d prompts, vocabulary %d, first row %s" % (len(PROMPTS), out["vocab_size"], tok[0, :12].tolist()))
+
+
 def main():
     mg._install_shims()
     sys.path.insert(0, mg.REF)
     os.chdir(mg.REF)
     import models.base  # noqa: F401
     torch.set_grad_enabled(False)
-    todo = sys.argv[1:] or (list(MULTI) + list(ZEROSHOT) + ["meter", "lr_policy", "train_b16_16x32", "cpu_speed"])
+    todo = sys.argv[1:] or (list(MULTI) + list(ZEROSHOT) + ["meter", "lr_policy", "train_b16_16x32", "cpu_speed", "tokenizer"])
     for n in todo:
         if n in MULTI:
             run_multi(n)
@@ -285,6 +313,8 @@ def main():
             run_train_full()
         elif n == "cpu_speed":
             run_cpu_speed()
+        elif n == "tokenizer":
+            run_tokenizer()
         else:
             raise SystemExit("unknown case " + n)
 

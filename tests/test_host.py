@@ -264,3 +264,53 @@ def test_kcat_layout_and_weight_algebra():
         u = a2 @ d["i2t_cat_w"].t() + d["i2t_cat_b"]
         want_u = lin(mid_pre, "dist_net.integration2temporal_nets.%d.linear_fuse" % i)
         assert float((u[1:] - want_u[1:]).abs().max()) < 2e-6                       # patch rows only (the class row is never read)
+
+
+def test_torchscript_archive_ingest(tmp_path):
+    """OpenAI publishes CLIP as TorchScript archives; the reference reads them with ``torch.jit.load(...).state_dict()``
+    (``clip.py:618-623``).  A scripted module with CLIP-shaped parameter names goes through the same path here."""
+    import torch.nn as nn
+    from dist_b200.utils import checkpoint
+
+    class Block(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.ln_1 = nn.LayerNorm(8)
+
+        def forward(self, x):
+            return self.ln_1(x)
+
+    class Visual(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.conv1 = nn.Conv2d(3, 8, 4, 4, bias=False)
+            self.class_embedding = nn.Parameter(torch.randn(8))
+            self.proj = nn.Parameter(torch.randn(8, 6))
+            self.resblock = Block()
+
+        def forward(self, x):
+            return self.resblock(self.conv1(x).flatten(2).transpose(1, 2)) @ self.proj + self.class_embedding.sum()
+
+    class Clip(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.visual = Visual()
+            self.logit_scale = nn.Parameter(torch.ones([]) * 2.6593)
+            self.register_buffer("input_resolution", torch.tensor(8))
+
+        def forward(self, x):
+            return self.visual(x) * self.logit_scale.exp()
+
+    torch.manual_seed(0)
+    m = Clip().eval()
+    path = str(tmp_path / "ViT-tiny.pt")
+    torch.jit.script(m).save(path)
+    sd = checkpoint.load_state_dict(path)
+    want = m.state_dict()
+    assert set(sd) == set(want) and all(torch.equal(sd[k], want[k]) for k in want)
+    assert {"visual.conv1.weight", "visual.class_embedding", "visual.proj", "visual.resblock.ln_1.weight", "logit_scale"} <= set(sd)
+    # a plain state_dict saved under a .pt name (no TorchScript) falls back to torch.load
+    plain = str(tmp_path / "plain.pt")
+    torch.save(want, plain)
+    sd2 = checkpoint.load_state_dict(plain)
+    assert set(sd2) == set(want)
