@@ -27,8 +27,19 @@ namespace {
 constexpr int HD = 64;
 constexpr int QT = 128;                 // query rows per tile
 constexpr int Q_RING = 4;
-constexpr int KV_STAGES = 2;
+#ifndef DISTB200_ATT_KV_STAGES
+#define DISTB200_ATT_KV_STAGES 2
+#endif
+constexpr int KV_STAGES = DISTB200_ATT_KV_STAGES;
 constexpr int ATT_THREADS = 352;
+#ifndef DISTB200_ATT_HELD
+#define DISTB200_ATT_HELD 1                // measured (B200, 197 / 257 tokens): 0 -> 0.117 / 0.897 ms, 1 -> 0.104 / 0.828 ms, 2 -> 0.131 / 0.986 ms (spills
+                                          // at the 168-register cap of 11 warps), 3 -> 0.145 / 1.441 ms
+#endif
+#ifndef DISTB200_ATT_SETMAXNREG
+#define DISTB200_ATT_SETMAXNREG 0         // tried: ptxas then spills in every role (even HELD = 1: 424 bytes), slower
+#endif
+constexpr int HELD = DISTB200_ATT_HELD;       // 32-column score chunks kept in registers between the two softmax passes
 constexpr uint32_t Q_TILE_BYTES = QT * HD * 2;
 
 struct alignas(64) AttArgs {
@@ -42,7 +53,18 @@ struct alignas(64) AttArgs {
     int slot_cols, o_col, n_slots;
     int split_col;                      // S columns [0, split_col) are consumed before O (which aliases the S tail) may be written
     long long items;                    // frames * heads
+    int dbg;                            // -DDISTB200_ATT_PROBES + DISTB200_ATT_DBG: 1 no max pass, 2 no exponentials, 4 no O read-out, 8 no P write-back, 16 no loads
 };
+
+// Bottleneck probes and a clock64 timeline (tools/trace_attention.py), compiled in only with -DDISTB200_ATT_PROBES.
+#ifdef DISTB200_ATT_PROBES
+#define ATT_PROBE(bit) (args.dbg & (bit))
+__device__ long long* g_att_trace = nullptr;      // [cta][tile < 64][16]
+#define ATT_STAMP(g, slot) do { if (g_att_trace && (g) < 64) g_att_trace[((long long)blockIdx.x * 64 + (g)) * 16 + (slot)] = clock64(); } while (0)
+#else
+#define ATT_PROBE(bit) false
+#define ATT_STAMP(g, slot) do { } while (0)
+#endif
 
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* v) {
     asm volatile(
@@ -126,6 +148,12 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_tc_kernel(const __gr
     if ((long long)blockIdx.x >= args.items) my_items = 0;
     const long long total = my_items * QTn;             // tiles of this CTA, g = item_index * q_tiles + qt
 
+    // Register split (setmaxnreg): the three issuing warps need a few dozen registers, the softmax warps keep HELD x 32 scores per
+    // thread between their two passes.  11 warps x 168 >= 8 x 200 + 3 x 80.
+#if DISTB200_ATT_SETMAXNREG
+    if (warp >= 8) asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
+    else asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
+#endif
     if (warp == 8) {
         // ===================== TMA producer =====================
         if (lane == 0) {
@@ -137,13 +165,13 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_tc_kernel(const __gr
                 const int st = it % KV_STAGES;
                 const uint32_t ph = (uint32_t)(it / KV_STAGES) & 1u;
                 ptx::mbar_wait(b.kv_empty + 8 * st, ph ^ 1u);
-                ptx::mbar_arrive_expect_tx(b.kv_full + 8 * st, 2 * kv_bytes);
+                if (ATT_PROBE(16)) ptx::mbar_arrive(b.kv_full + 8 * st); else ptx::mbar_arrive_expect_tx(b.kv_full + 8 * st, 2 * kv_bytes);
                 const uint32_t sk = s_kv + (uint32_t)st * 2 * kv_bytes, sv = sk + kv_bytes;
-                for (int i = 0; i < boxes64; ++i) {
+                for (int i = 0; i < (ATT_PROBE(16) ? 0 : boxes64); ++i) {
                     ptx::tma_load_3d(sk + i * 64 * HD * 2, &args.tm64, b.kv_full + 8 * st, D + h * HD, i * 64, f);
                     ptx::tma_load_3d(sv + i * 64 * HD * 2, &args.tm64, b.kv_full + 8 * st, 2 * D + h * HD, i * 64, f);
                 }
-                for (int i = 0; i < tail16; ++i) {
+                for (int i = 0; i < (ATT_PROBE(16) ? 0 : tail16); ++i) {
                     const int r = boxes64 * 64 + i * 16;
                     ptx::tma_load_3d(sk + r * HD * 2, &args.tm16, b.kv_full + 8 * st, D + h * HD, r, f);
                     ptx::tma_load_3d(sv + r * HD * 2, &args.tm16, b.kv_full + 8 * st, 2 * D + h * HD, r, f);
@@ -152,6 +180,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_tc_kernel(const __gr
                     const int qs = (int)(g % Q_RING);
                     const uint32_t qph = (uint32_t)(g / Q_RING) & 1u;
                     ptx::mbar_wait(b.q_empty + 8 * qs, qph ^ 1u);
+                    if (ATT_PROBE(16)) { ptx::mbar_arrive(b.q_full + 8 * qs); continue; }
                     ptx::mbar_arrive_expect_tx(b.q_full + 8 * qs, Q_TILE_BYTES);
                     ptx::tma_load_3d(s_q + qs * Q_TILE_BYTES, &args.tm64, b.q_full + 8 * qs, h * HD, qt * QT, f);
                     ptx::tma_load_3d(s_q + qs * Q_TILE_BYTES + 64 * HD * 2, &args.tm64, b.q_full + 8 * qs, h * HD, qt * QT + 64, f);
@@ -166,8 +195,10 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_tc_kernel(const __gr
                 const int st = it % KV_STAGES, qs = (int)(g % Q_RING), slot = (int)(g % (uint32_t)ns);
                 if (qt == 0) ptx::mbar_wait(b.kv_full + 8 * st, (uint32_t)(it / KV_STAGES) & 1u);
                 ptx::mbar_wait(b.q_full + 8 * qs, (uint32_t)(g / Q_RING) & 1u);
+                ATT_STAMP(g, 0);
                 ptx::mbar_wait(b.slot_free + 8 * slot, ((uint32_t)(g / ns) & 1u) ^ 1u);
                 ptx::tc_fence_after();
+                ATT_STAMP(g, 1);
                 const uint32_t sk = s_kv + (uint32_t)st * 2 * kv_bytes;
                 const uint64_t dq = ptx::umma_desc_k_sw128(s_q + qs * Q_TILE_BYTES);
                 const uint32_t ts = tmem + (uint32_t)(slot * args.slot_cols);
@@ -206,6 +237,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_tc_kernel(const __gr
                 }
                 ptx::mbar_wait(b.p_full + 8 * slot, ph);
                 ptx::tc_fence_after();
+                ATT_STAMP(g, 2);
                 for (int ks = ks_split; ks < ksteps_pv; ++ks) {
                     const uint64_t dv = ptx::umma_desc_k_sw128(sv + (uint32_t)ks * 16 * HD * 2);
                     mma_f16_ts(ts + (uint32_t)args.o_col, ts + (uint32_t)(8 * ks), dv, idesc_pv, ks != 0);
@@ -236,8 +268,10 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_tc_kernel(const __gr
                 const uint32_t ph = use & 1u;
                 const int row = qt * QT + w4 * 32 + lane;
                 const bool warp_has_rows = qt * QT + w4 * 32 < NR;
+                if (w4 == 0 && lane == 0) ATT_STAMP(g, 4);
                 ptx::mbar_wait(b.s_full + 8 * grp, ph);
                 ptx::tc_fence_after();
+                if (w4 == 0 && lane == 0) ATT_STAMP(g, 5);
                 float sum = 0.f;
                 float s_x = -INFINITY, p_x = 0.f;
                 if (args.odd) {
@@ -267,7 +301,25 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_tc_kernel(const __gr
                 if (warp_has_rows) {
                     // pass 1: row maximum over the valid keys
                     float mx = s_x;
-                    for (int c0 = 0; c0 < full_end; c0 += 32) {
+                    if (ATT_PROBE(1)) mx = 4.0f;
+                    // The kernel is bound by TMEM read bandwidth (tcgen05.ld: ~64 B / clock / SM; every score is read in both passes,
+                    // tools/trace_attention.py): the first HELD chunks of the row stay in registers between the passes.
+                    uint32_t hold[HELD][32];
+#pragma unroll
+                    for (int hc = 0; hc < HELD; ++hc) {
+                        if (32 * hc < full_end) {
+                            ptx::tmem_ld32(ts + (uint32_t)(32 * hc), hold[hc]);
+                            ptx::tmem_ld_wait();
+                            float m0 = __uint_as_float(hold[hc][0]), m1 = __uint_as_float(hold[hc][1]);
+#pragma unroll
+                            for (int i = 2; i < 32; i += 2) {
+                                m0 = fmaxf(m0, __uint_as_float(hold[hc][i]));
+                                m1 = fmaxf(m1, __uint_as_float(hold[hc][i + 1]));
+                            }
+                            mx = fmaxf(mx, fmaxf(m0, m1));
+                        }
+                    }
+                    for (int c0 = 32 * HELD; c0 < (ATT_PROBE(1) ? 0 : full_end); c0 += 32) {
                         uint32_t v[32];
                         ptx::tmem_ld32(ts + (uint32_t)c0, v);
                         ptx::tmem_ld_wait();
@@ -289,24 +341,41 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_tc_kernel(const __gr
                         for (int i = 0; i < 32; ++i)
                             if (full_end + i < N && (i < 16 || two)) mx = fmaxf(mx, __uint_as_float(v[i]));
                     }
+                    if (w4 == 0 && lane == 0) ATT_STAMP(g, 6);
                     // pass 2: p = 2^(s*c - max*c), bf16 pairs written back over S; fp32 row sum
                     const float mxs = mx * c;
                     float s0 = 0.f, s1 = 0.f;
-                    for (int c0 = 0; c0 < full_end; c0 += 32) {
+#pragma unroll
+                    for (int hc = 0; hc < HELD; ++hc) {
+                        if (32 * hc < full_end) {
+                            uint32_t p[16];
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) {
+                                const float e0 = fast_exp2(fmaf(__uint_as_float(hold[hc][2 * i]), c, -mxs));
+                                const float e1 = fast_exp2(fmaf(__uint_as_float(hold[hc][2 * i + 1]), c, -mxs));
+                                s0 += e0;
+                                s1 += e1;
+                                p[i] = pack_bf16x2(e0, e1);
+                            }
+                            tmem_st16(ts + (uint32_t)(16 * hc), p);
+                        }
+                    }
+                    for (int c0 = 32 * HELD; c0 < full_end; c0 += 32) {
                         uint32_t v[32];
                         ptx::tmem_ld32(ts + (uint32_t)c0, v);
                         ptx::tmem_ld_wait();
                         uint32_t p[16];
 #pragma unroll
                         for (int i = 0; i < 16; ++i) {
-                            const float e0 = fast_exp2(fmaf(__uint_as_float(v[2 * i]), c, -mxs));
-                            const float e1 = fast_exp2(fmaf(__uint_as_float(v[2 * i + 1]), c, -mxs));
+                            const float a0 = fmaf(__uint_as_float(v[2 * i]), c, -mxs), a1 = fmaf(__uint_as_float(v[2 * i + 1]), c, -mxs);
+                            const float e0 = ATT_PROBE(2) ? a0 : fast_exp2(a0);
+                            const float e1 = ATT_PROBE(2) ? a1 : fast_exp2(a1);
                             s0 += e0;
                             s1 += e1;
                             p[i] = pack_bf16x2(e0, e1);
                         }
                         // keys [c0, c0+32) -> 16 packed columns at c0/2: always behind the S read front of this lane
-                        tmem_st16(ts + (uint32_t)(c0 >> 1), p);
+                        if (!ATT_PROBE(8)) tmem_st16(ts + (uint32_t)(c0 >> 1), p);
                         if (c0 + 32 == args.split_col && args.split_col < args.keys_pad) {      // first batch of P is complete
                             ptx::tmem_st_wait();
                             ptx::tc_fence_before();
@@ -339,10 +408,12 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_tc_kernel(const __gr
                     ptx::mbar_arrive(b.p_early + 8 * grp);             // a warp without rows still signs the early batch
                 }
                 ptx::tc_fence_before();
+                if (w4 == 0 && lane == 0) ATT_STAMP(g, 7);
                 ptx::mbar_arrive(b.p_full + 8 * grp);
                 ptx::mbar_wait(b.o_full + 8 * grp, ph);
                 ptx::tc_fence_after();
-                if (warp_has_rows) {
+                if (w4 == 0 && lane == 0) ATT_STAMP(g, 8);
+                if (warp_has_rows && !ATT_PROBE(4)) {
                     const float inv = 1.f / sum;
                     bf16* dst_row = args.out + ((long long)f * NR + row) * D + h * HD;
 #pragma unroll
@@ -378,6 +449,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_tc_kernel(const __gr
                 }
                 if (args.odd && qt == (int)qtn - 1) ptx::mbar_arrive(b.kv_empty + 8 * (uint32_t)(it % KV_STAGES));
                 ptx::tc_fence_before();
+                if (w4 == 0 && lane == 0) ATT_STAMP(g, 9);
                 ptx::mbar_arrive(b.slot_free + 8 * grp);
             }
         }
@@ -396,6 +468,12 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 
 }  // namespace
 
+#ifdef DISTB200_ATT_PROBES
+extern "C" int distb200_debug_att_trace(long long* buf) {
+    cudaMemcpyToSymbol(g_att_trace, &buf, sizeof(buf));
+    return 0;
+}
+#endif
 int attention_tc_launch(const void* qkv, void* out, int frames, int tokens, int heads, cudaStream_t stream) {
     int keys_pad = (tokens + 15) / 16 * 16;
     const int keys_ld = keys_pad;
@@ -447,6 +525,10 @@ int attention_tc_launch(const void* qkv, void* out, int frames, int tokens, int 
     args.split_col = (args.o_col + HD + 31) / 32 * 32;       // first 32-column chunk boundary past the O region
     if (args.split_col > (tokens - args.odd) / 32 * 32 || args.o_col >= keys_pad) args.split_col = keys_pad;      // no chunk boundary there: one batch
     args.items = (long long)frames * heads;
+    args.dbg = 0;
+#ifdef DISTB200_ATT_PROBES
+    args.dbg = getenv("DISTB200_ATT_DBG") ? atoi(getenv("DISTB200_ATT_DBG")) : 0;
+#endif
     DISTB200_REQUIRE(args.items * args.q_tiles < (1ll << 31), "attention(tcgen05): too many tiles");
     const int smem = Q_RING * (int)Q_TILE_BYTES + KV_STAGES * 2 * keys_ld * HD * 2 + 1024;
     static int smem_set_dev[DISTB200_MAX_DEVICES] = {};
