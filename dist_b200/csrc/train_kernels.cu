@@ -168,15 +168,34 @@ __global__ void __launch_bounds__(256) colsum_kernel(const void* src, int dtype,
 // column and block).
 // ---------------------------------------------------------------------------------------------------
 constexpr int LNB_MAXV = 8;      // widest row: 128 * LNB_MAXV columns
-constexpr int LNB_WARPS = 8;
+constexpr int LNB_WARPS = 4;
 
-template <int LNB_V>
+// gradient rows arrive in bf16 (tensor-core path) or fp32 (parity path): keep them packed in registers until they are used
+template <bool BF> struct DyRaw;
+template <> struct DyRaw<true> {
+    typedef uint2 T;
+    static __device__ __forceinline__ T load(const void* p, long long i) { return *reinterpret_cast<const uint2*>(reinterpret_cast<const bf16*>(p) + i); }
+    static __device__ __forceinline__ float4 get(const T& u) {
+        return make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u), __uint_as_float(u.y << 16), __uint_as_float(u.y & 0xffff0000u));
+    }
+};
+template <> struct DyRaw<false> {
+    typedef float4 T;
+    static __device__ __forceinline__ T load(const void* p, long long i) { return *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p) + i); }
+    static __device__ __forceinline__ float4 get(const T& u) { return u; }
+};
+
+// Every operand of a row (x, the periodic addend, both gradient rows, the skip gradient, the old dx when accumulating) is requested
+// at the top of the row's iteration: round 1 issued them in three dependent phases (x -> statistics -> gradients -> skip), which
+// left ~2 KB per warp in flight and 1.5 TB/s (23 % of HBM) on the IntegrationNetwork's double LayerNorm.
+template <int LNB_V, bool DYBF>
 __global__ void __launch_bounds__(LNB_WARPS * 32) layernorm_bwd_kernel(
     const float* __restrict__ in1, long long ld_in1, const float* __restrict__ in2, long long ld_in2, long long in2_period, long long rows, int cols,
     float eps, const float* __restrict__ g1, const void* dy1, long long ld_dy1, const float* __restrict__ g2, const void* dy2, long long ld_dy2,
-    int dy_dtype, const float* add, long long ld_add, float* dx, long long ld_dx, int accumulate, void* dx_lp, long long ld_dx_lp, int lp_dtype,
+    const float* add, long long ld_add, float* dx, long long ld_dx, int accumulate, void* dx_lp, long long ld_dx_lp, int lp_dtype,
     float* dg1, float* db1, float* dg2, float* db2, int rows_per_warp) {
     grid_dep_sync();
+    typedef DyRaw<DYBF> Dy;
     extern __shared__ float sh[];            // [4][cols]: dg1, db1, dg2, db2 partials of this block
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < 4 * cols; i += blockDim.x) sh[i] = 0.f;
@@ -186,6 +205,7 @@ __global__ void __launch_bounds__(LNB_WARPS * 32) layernorm_bwd_kernel(
     for (int i = 0; i < LNB_V; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) a_dg1[i][j] = a_db1[i][j] = a_dg2[i][j] = a_db2[i][j] = 0.f;
+    const bool rmw = dx && accumulate;
 
     const long long row_begin = ((long long)blockIdx.x * LNB_WARPS + warp) * rows_per_warp;
     for (int rr = 0; rr < rows_per_warp; ++rr) {
@@ -193,13 +213,25 @@ __global__ void __launch_bounds__(LNB_WARPS * 32) layernorm_bwd_kernel(
         if (row >= rows) break;
         const float* x = in1 + row * ld_in1;
         const float* x2 = in2 ? in2 + (row % in2_period) * ld_in2 : nullptr;
-        float4 v[LNB_V];
-        float sum = 0.f;
+        float4 v[LNB_V], ad[LNB_V], old[LNB_V];
+        typename Dy::T r1[LNB_V], r2[LNB_V];
+        // ---- all loads of the row
 #pragma unroll
         for (int i = 0; i < LNB_V; ++i) {
             const int c = (i * 32 + lane) * 4;
             if (c < cols) {
                 v[i] = *reinterpret_cast<const float4*>(x + c);
+                r1[i] = Dy::load(dy1, row * ld_dy1 + c);
+                if (dy2) r2[i] = Dy::load(dy2, row * ld_dy2 + c);
+                if (add) ad[i] = *reinterpret_cast<const float4*>(add + row * ld_add + c);
+                if (rmw) old[i] = *reinterpret_cast<const float4*>(dx + row * ld_dx + c);
+            }
+        }
+        float sum = 0.f;
+#pragma unroll
+        for (int i = 0; i < LNB_V; ++i) {
+            const int c = (i * 32 + lane) * 4;
+            if (c < cols) {
                 if (x2) {
                     const float4 w = *reinterpret_cast<const float4*>(x2 + c);
                     v[i].x += w.x; v[i].y += w.y; v[i].z += w.z; v[i].w += w.w;
@@ -226,13 +258,13 @@ __global__ void __launch_bounds__(LNB_WARPS * 32) layernorm_bwd_kernel(
             const int c = (i * 32 + lane) * 4;
             if (c < cols) {
                 v[i].x *= rstd; v[i].y *= rstd; v[i].z *= rstd; v[i].w *= rstd;          // xhat
-                const float4 d1 = ld4_any(dy1, dy_dtype, row * ld_dy1 + c);
+                const float4 d1 = Dy::get(r1[i]);
                 const float4 ga = *reinterpret_cast<const float4*>(g1 + c);
                 g[i] = make_float4(d1.x * ga.x, d1.y * ga.y, d1.z * ga.z, d1.w * ga.w);
                 a_dg1[i][0] += d1.x * v[i].x; a_dg1[i][1] += d1.y * v[i].y; a_dg1[i][2] += d1.z * v[i].z; a_dg1[i][3] += d1.w * v[i].w;
                 a_db1[i][0] += d1.x; a_db1[i][1] += d1.y; a_db1[i][2] += d1.z; a_db1[i][3] += d1.w;
                 if (dy2) {
-                    const float4 d2 = ld4_any(dy2, dy_dtype, row * ld_dy2 + c);
+                    const float4 d2 = Dy::get(r2[i]);
                     const float4 gb = *reinterpret_cast<const float4*>(g2 + c);
                     g[i].x += d2.x * gb.x; g[i].y += d2.y * gb.y; g[i].z += d2.z * gb.z; g[i].w += d2.w * gb.w;
                     a_dg2[i][0] += d2.x * v[i].x; a_dg2[i][1] += d2.y * v[i].y; a_dg2[i][2] += d2.z * v[i].z; a_dg2[i][3] += d2.w * v[i].w;
@@ -249,18 +281,9 @@ __global__ void __launch_bounds__(LNB_WARPS * 32) layernorm_bwd_kernel(
             if (c < cols) {
                 float4 o = make_float4(rstd * (g[i].x - mg - v[i].x * mgx), rstd * (g[i].y - mg - v[i].y * mgx),
                                        rstd * (g[i].z - mg - v[i].z * mgx), rstd * (g[i].w - mg - v[i].w * mgx));
-                if (add) {
-                    const float4 a = *reinterpret_cast<const float4*>(add + row * ld_add + c);
-                    o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
-                }
-                if (dx) {
-                    float4* p = reinterpret_cast<float4*>(dx + row * ld_dx + c);
-                    if (accumulate) {
-                        const float4 a = *p;
-                        o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
-                    }
-                    *p = o;
-                }
+                if (add) { o.x += ad[i].x; o.y += ad[i].y; o.z += ad[i].z; o.w += ad[i].w; }
+                if (rmw) { o.x += old[i].x; o.y += old[i].y; o.z += old[i].z; o.w += old[i].w; }
+                if (dx) *reinterpret_cast<float4*>(dx + row * ld_dx + c) = o;
                 if (dx_lp) st4_any(dx_lp, lp_dtype, row * ld_dx_lp + c, o);
             }
         }
@@ -556,16 +579,23 @@ extern "C" int distb200_layernorm_bwd(const float* in1, int64_t ld_in1, const fl
     DISTB200_REQUIRE(DISTB200_DTYPE_OK(dy_dtype) && DISTB200_DTYPE_OK(lp_dtype), "layernorm_bwd: bad dtype");
     if (!in2) in2_period = 1;
     DISTB200_REQUIRE(in2_period >= 1, "layernorm_bwd: in2_period must be >= 1");
-    // enough rows per warp to amortise the block-level parameter-gradient reduction, enough blocks to fill the GPU
-    long long warps = (long long)sm_count() * 4 * LNB_WARPS;
-    int rows_per_warp = (int)((rows + warps - 1) / warps);
-    if (rows_per_warp < 1) rows_per_warp = 1;
-    const long long blocks = (rows + (long long)LNB_WARPS * rows_per_warp - 1) / ((long long)LNB_WARPS * rows_per_warp);
     const size_t smem = (size_t)4 * cols * sizeof(float);
-#define DISTB200_LNB(V)                                                                                                                  \
-    DISTB200_LAUNCH(layernorm_bwd_kernel<V>, (unsigned)blocks, LNB_WARPS * 32, smem, (cudaStream_t)stream,                                           \
-        in1, ld_in1, in2, ld_in2, in2_period, rows, cols, eps, g1, dy1, ld_dy1, g2, dy2, ld_dy2, dy_dtype, add, ld_add, dx, ld_dx, accumulate, dx_lp, \
-        ld_dx_lp, lp_dtype, dg1, db1, dg2, db2, rows_per_warp)
+    // one wave of resident blocks (the register footprint, and with it the residency, follows the row width): every warp walks
+    // rows_per_warp consecutive rows, which amortises the block-level reduction of the parameter gradients
+#define DISTB200_LNB2(V, BF)                                                                                                            \
+    do {                                                                                                                                \
+        int per_sm = 1;                                                                                                                 \
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, layernorm_bwd_kernel<V, BF>, LNB_WARPS * 32, smem);                     \
+        if (per_sm < 1) per_sm = 1;                                                                                                     \
+        const long long warps = (long long)sm_count() * per_sm * LNB_WARPS;                                                            \
+        int rows_per_warp = (int)((rows + warps - 1) / warps);                                                                          \
+        if (rows_per_warp < 1) rows_per_warp = 1;                                                                                       \
+        const long long blocks = (rows + (long long)LNB_WARPS * rows_per_warp - 1) / ((long long)LNB_WARPS * rows_per_warp);            \
+        DISTB200_LAUNCH((layernorm_bwd_kernel<V, BF>), (unsigned)blocks, LNB_WARPS * 32, smem, (cudaStream_t)stream,                                  \
+            in1, ld_in1, in2, ld_in2, in2_period, rows, cols, eps, g1, dy1, ld_dy1, g2, dy2, ld_dy2, add, ld_add, dx, ld_dx, accumulate, dx_lp,  \
+            ld_dx_lp, lp_dtype, dg1, db1, dg2, db2, rows_per_warp);                                                                     \
+    } while (0)
+#define DISTB200_LNB(V) do { if (dy_dtype == DISTB200_BF16) DISTB200_LNB2(V, true); else DISTB200_LNB2(V, false); } while (0)
     // float4 per lane: the register footprint (and with it the number of resident warps) follows the row width
     if (cols <= 128) DISTB200_LNB(1);
     else if (cols <= 256) DISTB200_LNB(2);
@@ -573,6 +603,7 @@ extern "C" int distb200_layernorm_bwd(const float* in1, int64_t ld_in1, const fl
     else if (cols <= 512) DISTB200_LNB(4);
     else if (cols <= 768) DISTB200_LNB(6);
     else DISTB200_LNB(8);
+#undef DISTB200_LNB2
 #undef DISTB200_LNB
     return check_launch("layernorm_bwd");
 }

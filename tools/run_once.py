@@ -20,6 +20,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--workload", default="b16_8x16")
 ap.add_argument("--clips", type=int, default=32)
 ap.add_argument("--precision", default="bf16")
+ap.add_argument("--names", default="", help="write the call names of the plan (launch order) to this JSON file")
 a = ap.parse_args()
 arch = DistArch(**WORKLOADS[a.workload]["arch"]).validate()
 sd = synth.synth_state_dict(arch, seed=0)
@@ -31,3 +32,6 @@ eng.forward(use_graph=False)
 torch.cuda.synchronize()
 torch.cuda.profiler.stop()
 print("ok", [c.name for c in eng.calls[:32]])
+if a.names:
+    import json
+    json.dump([c.name for c in eng.calls], open(a.names, "w"))
