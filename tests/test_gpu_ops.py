@@ -195,6 +195,27 @@ def test_attention(tokens, heads, frames, mode):
     assert rel_l2(out.float(), exp) < (3e-6 if dtype == torch.float32 else 6e-3)
 
 
+@pytest.mark.parametrize("tokens,heads,frames", [(197, 12, 64), (257, 16, 40), (16, 1, 3), (33, 2, 200), (100, 3, 7), (128, 2, 90), (129, 2, 90),
+                                                 (225, 4, 50), (241, 4, 50), (273, 4, 50), (288, 2, 80)])
+def test_attention_tc_layouts(tokens, heads, frames):
+    """Every TMEM plan of the tensor-core kernel (two slots + dedicated O, O in the other slot, odd key on the CUDA cores, one slot),
+    several items per CTA so that the slot / ring phases wrap; rows with a dominant key (exponent range) and NaN-free output."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(tokens * 7 + heads)
+    qkv = (torch.randn(frames, tokens, 3 * heads * 64, generator=g) * 1.5)
+    qkv[:, tokens // 2, :heads * 64] *= 6.0                    # a query row with a very peaked distribution
+    qkv = qkv.to(DEV, torch.bfloat16)
+    out = torch.full((frames, tokens, heads * 64), float("nan"), device=DEV, dtype=torch.bfloat16)
+    call = ops.attention(qkv, out, frames, tokens, heads)
+    _run(call)
+    exp = _attention_ref(qkv, frames, tokens, heads)
+    assert bool(torch.isfinite(out.float()).all())
+    assert rel_l2(out.float(), exp) < 6e-3
+    first = out.clone()
+    _run(call)
+    assert torch.equal(first, out)                             # replay is bit-identical
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("keys,batch", [(197, 9), (8, 3), (257, 2)])
 def test_cross_attention(dtype, keys, batch):

@@ -20,13 +20,18 @@ ap.add_argument("--build", action="store_true")
 ap.add_argument("--tokens", type=int, default=197)
 ap.add_argument("--heads", type=int, default=12)
 ap.add_argument("--frames", type=int, default=256)
+ap.add_argument("--lib", default=LIB)
+ap.add_argument("--first", type=int, default=0)
+ap.add_argument("--count", type=int, default=12)
+ap.add_argument("--cta", type=int, default=0)
 a = ap.parse_args()
 if a.build:
     from dist_b200 import build as b
     subprocess.run(["nvcc"] + b.NVCC_FLAGS + ["-DDISTB200_ATT_PROBES", "-o", LIB] + b.sources(), check=True)
     print(LIB)
     sys.exit(0)
-os.environ["DISTB200_LIB"] = LIB
+os.environ["DISTB200_LIB"] = a.lib
+os.environ["DISTB200_ALLOW_STALE"] = "1"
 import torch
 from dist_b200 import ops
 L = ops.lib()
@@ -44,9 +49,9 @@ call.launch(s.cuda_stream)
 torch.cuda.synchronize()
 L.distb200_debug_att_trace(None)
 tr = trace.cpu().view(148, 64, 16)
-rows = tr[0]
+rows = tr[a.cta]
 t0 = int(rows[rows > 0].min())
-for g in range(12):
+for g in range(a.first, min(64, a.first + a.count)):
     if int(rows[g].max()) == 0:
         break
     ev = sorted((int(rows[g][k]) - t0, n) for k, n in SLOTS.items() if int(rows[g][k]) > 0)
