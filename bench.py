@@ -535,9 +535,12 @@ def run_infer(args, arch, wl, world, rank, local, dev, light=False):
         if "dist.tn" in by_name:
             tn = by_name["dist.tn"]
             gbs = tn["bytes"] / (tn["ms"] / 1e3) / 1e9
+            tn_traffic = None
+            if os.path.exists(tpath):
+                tn_traffic = json.load(open(tpath)).get("%s/dist.tn/%d" % (args.workload, b), {}).get("dram_bytes_per_launch")
             roofline_hbm = {"bound": "hbm", "kernel": "temporalnet_kernel @ dist.tn (%d launches per step)" % tn["launches"], "achieved": gbs,
                             "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"], "bytes_per_launch": tn["bytes"] // max(tn["launches"], 1),
-                            "us_per_launch": 1e3 * tn["ms"] / max(tn["launches"], 1), "traffic": None,
+                            "us_per_launch": 1e3 * tn["ms"] / max(tn["launches"], 1), "traffic": tn_traffic,
                             "note": "SIMT-issue / LSU bound, not HBM bound (DESIGN.md 4.7): the fraction is reported against the HBM roofline the north star names"}
         cpu = None
         if world > 1:
