@@ -94,6 +94,58 @@ __global__ void __launch_bounds__(256) group_sum_kernel(const void* src, int src
 // column sums: block = 32 columns x 8 row lanes; rows of all groups are split over blockIdx.y; one atomicAdd per
 // (block, column, period slot).  period > 1 (per-frame class tokens, positional embeddings) uses rows_per_group == 1.
 // ---------------------------------------------------------------------------------------------------
+// bf16, contiguous rows, period 1 (every bias gradient of the fine-tuning step): thread = 8 consecutive columns (one 16-byte load), cols / 8
+// threads per row and 256 / (cols / 8) rows per block pass, U independent loads in flight per thread.  The 4-column version below ran the
+// 96-wide gradients at 0.8-1.1 TB/s (24 of 32 lanes, 8-byte loads).
+template <int U, bool DENSE>
+__global__ void __launch_bounds__(256) colsum_bf16_dense_kernel(const uint4* __restrict__ src, long long ld8, unsigned total, long long roff, unsigned rpg,
+                                                                long long gstride, int tpr, int rpb, float* out, float* out2, unsigned rows_per_block) {
+    grid_dep_sync();
+    __shared__ float red[256][9];
+    const int tr = threadIdx.x / tpr, tc = threadIdx.x - tr * tpr;
+    const unsigned r_begin = blockIdx.x * rows_per_block;
+    unsigned r_end = r_begin + rows_per_block;
+    if (r_end > total) r_end = total;
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+    // DENSE: rows are contiguous from roff; otherwise row i of the walk is row (i / rpg) * gstride + roff + i % rpg of the matrix
+    auto addr = [&](unsigned i) -> const uint4* {
+        const long long srow = DENSE ? (long long)i + roff : (long long)(i / rpg) * gstride + roff + (long long)(i % rpg);
+        return src + srow * ld8 + tc;
+    };
+    auto add8 = [&](const uint4& v) {
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            acc[2 * e] += __uint_as_float(w[e] << 16);
+            acc[2 * e + 1] += __uint_as_float(w[e] & 0xffff0000u);
+        }
+    };
+    if (tr < rpb) {
+        unsigned i = r_begin + tr;
+        for (; i + (unsigned)((U - 1) * rpb) < r_end; i += (unsigned)(U * rpb)) {
+            uint4 v[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) v[u] = __ldg(addr(i + (unsigned)(u * rpb)));
+#pragma unroll
+            for (int u = 0; u < U; ++u) add8(v[u]);
+        }
+        for (; i < r_end; i += (unsigned)rpb) add8(__ldg(addr(i)));
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) red[threadIdx.x][e] = acc[e];
+    __syncthreads();
+    // thread (e, column vector): sums the row lanes of one column
+    for (int o = threadIdx.x; o < tpr * 8; o += 256) {
+        const int cv = o >> 3, e = o & 7;
+        float t = 0.f;
+        for (int j = 0; j < rpb; ++j) t += red[j * tpr + cv][e];
+        atomicAdd(out + o, t);
+        if (out2) atomicAdd(out2 + o, t);
+    }
+}
+
 __global__ void __launch_bounds__(256) colsum_kernel(const void* src, int dtype, long long ld, long long groups, long long rows_per_group,
                                                      long long gstride, long long roff, long long period, int cols, float* out, float* out2,
                                                      long long rows_per_block) {
@@ -188,7 +240,15 @@ template <> struct DyRaw<false> {
 // Every operand of a row (x, the periodic addend, both gradient rows, the skip gradient, the old dx when accumulating) is requested
 // at the top of the row's iteration: round 1 issued them in three dependent phases (x -> statistics -> gradients -> skip), which
 // left ~2 KB per warp in flight and 1.5 TB/s (23 % of HBM) on the IntegrationNetwork's double LayerNorm.
-template <int LNB_V, bool DYBF>
+// LPR lanes share a row (32, or 8 for rows of <= 128 columns: four rows per warp pass, three shuffle steps per reduction, every lane busy).
+template <int LPR>
+__device__ __forceinline__ float lanes_sum(float v) {
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+template <int LNB_V, bool DYBF, int LPR>
 __global__ void __launch_bounds__(LNB_WARPS * 32) layernorm_bwd_kernel(
     const float* __restrict__ in1, long long ld_in1, const float* __restrict__ in2, long long ld_in2, long long in2_period, long long rows, int cols,
     float eps, const float* __restrict__ g1, const void* dy1, long long ld_dy1, const float* __restrict__ g2, const void* dy2, long long ld_dy2,
@@ -198,6 +258,8 @@ __global__ void __launch_bounds__(LNB_WARPS * 32) layernorm_bwd_kernel(
     typedef DyRaw<DYBF> Dy;
     extern __shared__ float sh[];            // [4][cols]: dg1, db1, dg2, db2 partials of this block
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int RPW = 32 / LPR;                 // rows per warp pass
+    const int lc = lane % LPR, sub = lane / LPR;
     for (int i = threadIdx.x; i < 4 * cols; i += blockDim.x) sh[i] = 0.f;
     __syncthreads();
     float a_dg1[LNB_V][4], a_db1[LNB_V][4], a_dg2[LNB_V][4], a_db2[LNB_V][4];
@@ -208,18 +270,20 @@ __global__ void __launch_bounds__(LNB_WARPS * 32) layernorm_bwd_kernel(
     const bool rmw = dx && accumulate;
 
     const long long row_begin = ((long long)blockIdx.x * LNB_WARPS + warp) * rows_per_warp;
-    for (int rr = 0; rr < rows_per_warp; ++rr) {
-        const long long row = row_begin + rr;
-        if (row >= rows) break;
+    for (int rr = 0; rr < rows_per_warp; rr += RPW) {
+        if (row_begin + rr >= rows) break;
+        const long long row = row_begin + rr + sub;
+        const bool live = rr + sub < rows_per_warp && row < rows;      // lanes of a missing row still take part in the shuffles
         const float* x = in1 + row * ld_in1;
-        const float* x2 = in2 ? in2 + (row % in2_period) * ld_in2 : nullptr;
+        const float* x2 = in2 ? in2 + ((live ? row : 0) % in2_period) * ld_in2 : nullptr;
         float4 v[LNB_V], ad[LNB_V], old[LNB_V];
         typename Dy::T r1[LNB_V], r2[LNB_V];
         // ---- all loads of the row
 #pragma unroll
         for (int i = 0; i < LNB_V; ++i) {
-            const int c = (i * 32 + lane) * 4;
-            if (c < cols) {
+            const int c = (i * LPR + lc) * 4;
+            v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (c < cols && live) {
                 v[i] = *reinterpret_cast<const float4*>(x + c);
                 r1[i] = Dy::load(dy1, row * ld_dy1 + c);
                 if (dy2) r2[i] = Dy::load(dy2, row * ld_dy2 + c);
@@ -230,8 +294,8 @@ __global__ void __launch_bounds__(LNB_WARPS * 32) layernorm_bwd_kernel(
         float sum = 0.f;
 #pragma unroll
         for (int i = 0; i < LNB_V; ++i) {
-            const int c = (i * 32 + lane) * 4;
-            if (c < cols) {
+            const int c = (i * LPR + lc) * 4;
+            if (c < cols && live) {
                 if (x2) {
                     const float4 w = *reinterpret_cast<const float4*>(x2 + c);
                     v[i].x += w.x; v[i].y += w.y; v[i].z += w.z; v[i].w += w.w;
@@ -239,24 +303,24 @@ __global__ void __launch_bounds__(LNB_WARPS * 32) layernorm_bwd_kernel(
                 sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
             }
         }
-        const float mean = warp_sum(sum) / (float)cols;
+        const float mean = lanes_sum<LPR>(sum) / (float)cols;
         float sq = 0.f;
 #pragma unroll
         for (int i = 0; i < LNB_V; ++i) {
-            const int c = (i * 32 + lane) * 4;
-            if (c < cols) {
+            const int c = (i * LPR + lc) * 4;
+            if (c < cols && live) {
                 v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
                 sq += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
             }
         }
-        const float rstd = rsqrtf(warp_sum(sq) / (float)cols + eps);
+        const float rstd = rsqrtf(lanes_sum<LPR>(sq) / (float)cols + eps);
         // g = dy1*g1 + dy2*g2; accumulate parameter gradients; row means of g and g*xhat
         float4 g[LNB_V];
         float sg = 0.f, sgx = 0.f;
 #pragma unroll
         for (int i = 0; i < LNB_V; ++i) {
-            const int c = (i * 32 + lane) * 4;
-            if (c < cols) {
+            const int c = (i * LPR + lc) * 4;
+            if (c < cols && live) {
                 v[i].x *= rstd; v[i].y *= rstd; v[i].z *= rstd; v[i].w *= rstd;          // xhat
                 const float4 d1 = Dy::get(r1[i]);
                 const float4 ga = *reinterpret_cast<const float4*>(g1 + c);
@@ -274,11 +338,11 @@ __global__ void __launch_bounds__(LNB_WARPS * 32) layernorm_bwd_kernel(
                 sgx += (g[i].x * v[i].x + g[i].y * v[i].y) + (g[i].z * v[i].z + g[i].w * v[i].w);
             }
         }
-        const float mg = warp_sum(sg) / (float)cols, mgx = warp_sum(sgx) / (float)cols;
+        const float mg = lanes_sum<LPR>(sg) / (float)cols, mgx = lanes_sum<LPR>(sgx) / (float)cols;
 #pragma unroll
         for (int i = 0; i < LNB_V; ++i) {
-            const int c = (i * 32 + lane) * 4;
-            if (c < cols) {
+            const int c = (i * LPR + lc) * 4;
+            if (c < cols && live) {
                 float4 o = make_float4(rstd * (g[i].x - mg - v[i].x * mgx), rstd * (g[i].y - mg - v[i].y * mgx),
                                        rstd * (g[i].z - mg - v[i].z * mgx), rstd * (g[i].w - mg - v[i].w * mgx));
                 if (add) { o.x += ad[i].x; o.y += ad[i].y; o.z += ad[i].z; o.w += ad[i].w; }
@@ -291,7 +355,7 @@ __global__ void __launch_bounds__(LNB_WARPS * 32) layernorm_bwd_kernel(
     // block reduction of the parameter gradients
 #pragma unroll
     for (int i = 0; i < LNB_V; ++i) {
-        const int c = (i * 32 + lane) * 4;
+        const int c = (i * LPR + lc) * 4;
         if (c < cols) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -548,6 +612,20 @@ extern "C" int distb200_colsum(const void* src, int32_t src_dtype, int64_t ld, i
     DISTB200_REQUIRE(!out2 || period == 1, "colsum: the second output needs period == 1");
     const long long total = groups * rows_per_group;
     DISTB200_REQUIRE(total < (1ll << 31), "colsum: too many rows");
+    if (src_dtype == DISTB200_BF16 && period == 1 && cols % 8 == 0 && ld % 8 == 0 && cols <= 2048) {
+        const int tpr = cols / 8, rpb = 256 / tpr;
+        long long blocks = (long long)sm_count() * 6;
+        long long rpblk = (total + blocks - 1) / blocks;
+        if (rpblk < 8 * rpb) rpblk = 8 * rpb;
+        blocks = (total + rpblk - 1) / rpblk;
+        if (gstride == rows_per_group)
+            DISTB200_LAUNCH((colsum_bf16_dense_kernel<8, true>), (unsigned)blocks, 256, 0, (cudaStream_t)stream, reinterpret_cast<const uint4*>(src),
+                            (long long)(ld / 8), (unsigned)total, (long long)roff, (unsigned)rows_per_group, (long long)gstride, tpr, rpb, out, out2, (unsigned)rpblk);
+        else
+            DISTB200_LAUNCH((colsum_bf16_dense_kernel<8, false>), (unsigned)blocks, 256, 0, (cudaStream_t)stream, reinterpret_cast<const uint4*>(src),
+                            (long long)(ld / 8), (unsigned)total, (long long)roff, (unsigned)rows_per_group, (long long)gstride, tpr, rpb, out, out2, (unsigned)rpblk);
+        return check_launch("colsum");
+    }
     dim3 grid((unsigned)((cols / 4 + 31) / 32), 1);
     long long rows_per_block = total;
     if (period == 1) {
@@ -582,27 +660,31 @@ extern "C" int distb200_layernorm_bwd(const float* in1, int64_t ld_in1, const fl
     const size_t smem = (size_t)4 * cols * sizeof(float);
     // one wave of resident blocks (the register footprint, and with it the residency, follows the row width): every warp walks
     // rows_per_warp consecutive rows, which amortises the block-level reduction of the parameter gradients
-#define DISTB200_LNB2(V, BF)                                                                                                            \
+#define DISTB200_LNB2(V, BF, LPR)                                                                                                          \
     do {                                                                                                                                \
         int per_sm = 1;                                                                                                                 \
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, layernorm_bwd_kernel<V, BF>, LNB_WARPS * 32, smem);                     \
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, layernorm_bwd_kernel<V, BF, LPR>, LNB_WARPS * 32, smem);                     \
         if (per_sm < 1) per_sm = 1;                                                                                                     \
         const long long warps = (long long)sm_count() * per_sm * LNB_WARPS;                                                            \
         int rows_per_warp = (int)((rows + warps - 1) / warps);                                                                          \
         if (rows_per_warp < 1) rows_per_warp = 1;                                                                                       \
+        rows_per_warp = (rows_per_warp + 32 / LPR - 1) / (32 / LPR) * (32 / LPR);                                                       \
         const long long blocks = (rows + (long long)LNB_WARPS * rows_per_warp - 1) / ((long long)LNB_WARPS * rows_per_warp);            \
-        DISTB200_LAUNCH((layernorm_bwd_kernel<V, BF>), (unsigned)blocks, LNB_WARPS * 32, smem, (cudaStream_t)stream,                                  \
+        DISTB200_LAUNCH((layernorm_bwd_kernel<V, BF, LPR>), (unsigned)blocks, LNB_WARPS * 32, smem, (cudaStream_t)stream,                                  \
             in1, ld_in1, in2, ld_in2, in2_period, rows, cols, eps, g1, dy1, ld_dy1, g2, dy2, ld_dy2, add, ld_add, dx, ld_dx, accumulate, dx_lp,  \
             ld_dx_lp, lp_dtype, dg1, db1, dg2, db2, rows_per_warp);                                                                     \
     } while (0)
-#define DISTB200_LNB(V) do { if (dy_dtype == DISTB200_BF16) DISTB200_LNB2(V, true); else DISTB200_LNB2(V, false); } while (0)
+#define DISTB200_LNB(V, LPR) do { if (dy_dtype == DISTB200_BF16) DISTB200_LNB2(V, true, LPR); else DISTB200_LNB2(V, false, LPR); } while (0)
     // float4 per lane: the register footprint (and with it the number of resident warps) follows the row width
-    if (cols <= 128) DISTB200_LNB(1);
-    else if (cols <= 256) DISTB200_LNB(2);
-    else if (cols <= 384) DISTB200_LNB(3);
-    else if (cols <= 512) DISTB200_LNB(4);
-    else if (cols <= 768) DISTB200_LNB(6);
-    else DISTB200_LNB(8);
+    if (cols <= 32) DISTB200_LNB(1, 8);
+    else if (cols <= 64) DISTB200_LNB(2, 8);
+    else if (cols <= 96) DISTB200_LNB(3, 8);
+    else if (cols <= 128) DISTB200_LNB(4, 8);
+    else if (cols <= 256) DISTB200_LNB(2, 32);
+    else if (cols <= 384) DISTB200_LNB(3, 32);
+    else if (cols <= 512) DISTB200_LNB(4, 32);
+    else if (cols <= 768) DISTB200_LNB(6, 32);
+    else DISTB200_LNB(8, 32);
 #undef DISTB200_LNB2
 #undef DISTB200_LNB
     return check_launch("layernorm_bwd");

@@ -76,6 +76,35 @@ def test_colsum(dt):
     assert rel_l2(out, big.double().sum(dim=0)) < 1e-4
 
 
+@pytest.mark.parametrize("cols,ld,rows", [(96, 96, 100352), (96, 104, 4099), (384, 384, 50432), (1536, 1536, 3001), (2048, 2048, 129), (8, 8, 5), (768, 776, 1)])
+def test_colsum_dense_bf16(cols, ld, rows):
+    """The contiguous-rows bf16 path (16-byte loads, cols / 8 threads per row): every width class, a row pitch wider than the columns,
+    a row offset, the second output, accumulation into a non-zero buffer."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(cols + rows)
+    src = torch.randn(rows + 3, ld, generator=g).to(DEV, torch.bfloat16)
+    out = torch.full((cols,), 2.0, device=DEV)
+    out2 = torch.zeros(cols, device=DEV)
+    _run(ops.colsum(src, out, cols, ld=ld, groups=1, rows_per_group=rows, gstride=rows, roff=3, out2=out2))
+    want = src.double()[3:, :cols].sum(dim=0)
+    scale = float(src.double()[3:, :cols].abs().sum(dim=0).max())
+    assert float((out.double() - 2.0 - want).abs().max()) < 2e-6 * scale + 1e-6
+    assert float((out2.double() - want).abs().max()) < 2e-6 * scale + 1e-6
+
+
+@pytest.mark.parametrize("cols,tokens,frames", [(384, 197, 40), (96, 17, 300), (768, 50, 3)])
+def test_colsum_grouped_bf16(cols, tokens, frames):
+    """Patch rows only (the class-token row of every frame skipped): groups = frames, rows_per_group = tokens - 1, gstride = tokens, roff = 1."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(cols + tokens)
+    src = torch.randn(frames, tokens, cols, generator=g).to(DEV, torch.bfloat16)
+    out = torch.zeros(cols, device=DEV)
+    _run(ops.colsum(src, out, cols, groups=frames, rows_per_group=tokens - 1, gstride=tokens, roff=1))
+    want = src.double()[:, 1:].sum(dim=(0, 1))
+    scale = float(src.double()[:, 1:].abs().sum(dim=(0, 1)).max())
+    assert float((out.double() - want).abs().max()) < 2e-6 * scale + 1e-6
+
+
 @pytest.mark.parametrize("cols,rows", [(96, 1000), (384, 333), (768, 70), (128, 5)])
 @pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
 def test_layernorm_bwd(cols, rows, dt):
