@@ -50,6 +50,8 @@ struct alignas(64) AttArgs {
     int keys_pad;                       // keys on the tensor-core path (multiple of 16)
     int keys_ld;                        // K / V rows held in shared memory (tokens rounded up to 16)
     int odd;                            // 1: the last key (index keys_pad) is handled on the CUDA cores, see below
+    int single;                         // 1: the item's last tile holds ONE query row (tokens % 128 == 1): that row is computed on the CUDA cores
+    int cosign;                         // odd | single: the softmax threads read Q / K / V from shared memory and co-sign their release
     int slot_cols, o_col, n_slots;
     int split_col;                      // S columns [0, split_col) are consumed before O (which aliases the S tail) may be written
     long long items;                    // frames * heads
@@ -90,6 +92,77 @@ __device__ __forceinline__ float fast_exp2(float x) {
     return y;
 }
 
+// One query row against all keys of the item on the CUDA cores (see the call site): the 128 threads of a softmax group, Q row / K / V
+// tiles in their 128-byte-swizzled shared-memory layout.  The query row is re-read (broadcast) per key instead of living in 64
+// registers: the main loop runs at the register cap.
+__device__ __forceinline__ void single_row_tile(const uint8_t* qrow, const uint8_t* kbase, const uint8_t* vbase, float* P, float* red, float* osc,
+                                                int NR, int grp, bf16* dst) {
+    const int lane = threadIdx.x & 31, w4 = (threadIdx.x >> 5) & 3, t = w4 * 32 + lane;
+    const float c = 0.125f * 1.4426950408889634f;
+    float mx = -INFINITY;
+#pragma unroll 1
+    for (int k = t; k < NR; k += 128) {
+        const uint4* kr = reinterpret_cast<const uint4*>(kbase + k * 128);
+        float a0 = 0.f, a1 = 0.f;
+#pragma unroll 2
+        for (int j = 0; j < 8; ++j) {
+            const uint4 ka = kr[j ^ (k & 7)], qa = reinterpret_cast<const uint4*>(qrow)[j];       // row 0 of the Q tile: not swizzled
+            const uint32_t kw[4] = {ka.x, ka.y, ka.z, ka.w}, qw[4] = {qa.x, qa.y, qa.z, qa.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                a0 = fmaf(__uint_as_float(qw[e] << 16), __uint_as_float(kw[e] << 16), a0);
+                a1 = fmaf(__uint_as_float(qw[e] & 0xffff0000u), __uint_as_float(kw[e] & 0xffff0000u), a1);
+            }
+        }
+        const float sc = a0 + a1;
+        P[k] = sc;
+        mx = fmaxf(mx, sc);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0) red[w4] = mx;
+    asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory");
+    mx = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+    const float mxs1 = mx * c;
+    float part = 0.f;
+#pragma unroll 1
+    for (int k = t; k < NR; k += 128) {
+        const float e = fast_exp2(fmaf(P[k], c, -mxs1));
+        part += e;
+        P[k] = __bfloat162float(__float2bfloat16_rn(e));      // the tensor-core path multiplies bf16 probabilities too
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if (lane == 0) red[4 + w4] = part;
+    asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory");
+    const float inv1 = 1.f / ((red[4] + red[5]) + (red[6] + red[7]));
+    const int dg = t & 7, kg = t >> 3;                       // 8 output columns x one of 16 key groups
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+#pragma unroll 2
+    for (int k = kg; k < NR; k += 16) {
+        const float pk = P[k];
+        const uint4 va = reinterpret_cast<const uint4*>(vbase + k * 128)[dg ^ (k & 7)];
+        const uint32_t vw[4] = {va.x, va.y, va.z, va.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            acc[2 * e] = fmaf(pk, __uint_as_float(vw[e] << 16), acc[2 * e]);
+            acc[2 * e + 1] = fmaf(pk, __uint_as_float(vw[e] & 0xffff0000u), acc[2 * e + 1]);
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) osc[kg * HD + 8 * dg + e] = acc[e];
+    asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory");
+    if (t < HD) {
+        float o = 0.f;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) o += osc[j * HD + t];
+        dst[t] = __float2bfloat16_rn(o * inv1);
+    }
+    asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory");       // the scratch is free for this group's next single-row tile
+}
+
 struct Bars {   // shared-memory addresses of the mbarriers
     uint32_t kv_full, kv_empty, q_full, q_empty, s_full, p_full, o_full, slot_free, p_early;
 };
@@ -98,6 +171,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_tc_kernel(const __gr
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bar_mem[2 * KV_STAGES + 2 * Q_RING + 10];
     __shared__ uint32_t tmem_slot;
+    __shared__ float sr_p[2][288], sr_red[2][8], sr_o[2][16][HD];      // single-row tiles: scores / probabilities, reductions, partial outputs
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int D = args.heads * HD;
@@ -121,9 +195,9 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_tc_kernel(const __gr
             ptx::prefetch_tensormap(&args.tm64);
             ptx::prefetch_tensormap(&args.tm16);
             // odd-key mode: the epilogue of an item's last tile still reads the odd V row, so its 128 threads co-sign the release of K / V
-            for (int i = 0; i < KV_STAGES; ++i) { ptx::mbar_init(b.kv_full + 8 * i, 1); ptx::mbar_init(b.kv_empty + 8 * i, args.odd ? 129 : 1); }
+            for (int i = 0; i < KV_STAGES; ++i) { ptx::mbar_init(b.kv_full + 8 * i, 1); ptx::mbar_init(b.kv_empty + 8 * i, args.cosign ? 129 : 1); }
             // odd-key mode: the softmax threads read their Q row from shared memory, so they co-sign the release of a Q tile
-            for (int i = 0; i < Q_RING; ++i) { ptx::mbar_init(b.q_full + 8 * i, 1); ptx::mbar_init(b.q_empty + 8 * i, args.odd ? 129 : 1); }
+            for (int i = 0; i < Q_RING; ++i) { ptx::mbar_init(b.q_full + 8 * i, 1); ptx::mbar_init(b.q_empty + 8 * i, args.cosign ? 129 : 1); }
             for (int i = 0; i < 2; ++i) {
                 ptx::mbar_init(b.s_full + 8 * i, 1);
                 ptx::mbar_init(b.p_full + 8 * i, 128);
@@ -202,7 +276,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_tc_kernel(const __gr
                 const uint32_t sk = s_kv + (uint32_t)st * 2 * kv_bytes;
                 const uint64_t dq = ptx::umma_desc_k_sw128(s_q + qs * Q_TILE_BYTES);
                 const uint32_t ts = tmem + (uint32_t)(slot * args.slot_cols);
-                for (int n0 = 0; n0 < args.keys_pad; n0 += 256) {
+                const bool single = args.single && qt == QTn - 1;          // computed by the softmax group on the CUDA cores: no MMA, same hand-shakes
+                for (int n0 = 0; n0 < (single ? 0 : args.keys_pad); n0 += 256) {
                     const int nn = min(256, args.keys_pad - n0);
                     const uint32_t idesc = ptx::umma_idesc_bf16(QT, nn);
                     const uint64_t dk = ptx::umma_desc_k_sw128(sk + (uint32_t)n0 * HD * 2);
@@ -227,10 +302,11 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_tc_kernel(const __gr
                 const uint32_t sv = s_kv + (uint32_t)st * 2 * kv_bytes + kv_bytes;
                 const uint32_t ts = tmem + (uint32_t)(slot * args.slot_cols);
                 const int ks_split = args.split_col < args.keys_pad ? args.split_col / 16 : 0;
+                const bool single = args.single && qt == QTn - 1;
                 if (ks_split > 0) {
                     ptx::mbar_wait(b.p_early + 8 * slot, ph);
                     ptx::tc_fence_after();
-                    for (int ks = 0; ks < ks_split; ++ks) {
+                    for (int ks = 0; ks < (single ? 0 : ks_split); ++ks) {
                         const uint64_t dv = ptx::umma_desc_k_sw128(sv + (uint32_t)ks * 16 * HD * 2);
                         mma_f16_ts(ts + (uint32_t)args.o_col, ts + (uint32_t)(8 * ks), dv, idesc_pv, ks != 0);
                     }
@@ -238,7 +314,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_tc_kernel(const __gr
                 ptx::mbar_wait(b.p_full + 8 * slot, ph);
                 ptx::tc_fence_after();
                 ATT_STAMP(g, 2);
-                for (int ks = ks_split; ks < ksteps_pv; ++ks) {
+                for (int ks = ks_split; ks < (single ? 0 : ksteps_pv); ++ks) {
                     const uint64_t dv = ptx::umma_desc_k_sw128(sv + (uint32_t)ks * 16 * HD * 2);
                     mma_f16_ts(ts + (uint32_t)args.o_col, ts + (uint32_t)(8 * ks), dv, idesc_pv, ks != 0);
                 }
@@ -267,17 +343,28 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_tc_kernel(const __gr
                 const int h = (int)(item - f32i * heads32), f = (int)f32i;
                 const uint32_t ph = use & 1u;
                 const int row = qt * QT + w4 * 32 + lane;
-                const bool warp_has_rows = qt * QT + w4 * 32 < NR;
+                bool warp_has_rows = qt * QT + w4 * 32 < NR;
                 if (w4 == 0 && lane == 0) ATT_STAMP(g, 4);
                 ptx::mbar_wait(b.s_full + 8 * grp, ph);
                 ptx::tc_fence_after();
                 if (w4 == 0 && lane == 0) ATT_STAMP(g, 5);
                 float sum = 0.f;
                 float s_x = -INFINITY, p_x = 0.f;
-                if (args.odd) {
+                if (args.single && qt == (int)qtn - 1) {
+                    // A tile with ONE query row (257 = 2 x 128 + 1) would cost a full S-MMA -> softmax -> PV-MMA chain with one busy
+                    // thread.  The group's 128 threads compute the row on the CUDA cores instead, from the swizzled Q / K / V tiles in
+                    // shared memory: thread t scores keys t, t+128, ...; (8 columns x 16 key groups) for P V.  The mbarrier hand-shakes
+                    // of a normal tile are kept (the issuers skip their MMAs), so slot and ring phases stay in step.
+                    const int st = (int)(it % KV_STAGES), qs = (int)(g % Q_RING);
+                    const uint8_t* kbase = smem_raw + (s_kv - ptx::smem_u32(smem_raw)) + (uint32_t)st * 2 * kv_bytes;
+                    single_row_tile(smem_raw + (s_q - ptx::smem_u32(smem_raw)) + qs * Q_TILE_BYTES, kbase, kbase + kv_bytes, sr_p[grp], sr_red[grp],
+                                    &sr_o[grp][0][0], NR, grp, args.out + ((long long)f * NR + qt * QT) * D + h * HD);
+                    warp_has_rows = false;                    // from here on the tile behaves like one without rows
+                }
+                if (args.cosign) {
                     // The last key does not fit the TMEM budget of two slots (257 keys -> 272 fp32 columns): its score is one
                     // 64-term dot product per row on the CUDA cores, straight from the swizzled Q / K tiles in shared memory.
-                    if (warp_has_rows) {
+                    if (args.odd && warp_has_rows) {
                         const int st = (int)(it % KV_STAGES), qs = (int)(g % Q_RING);
                         const int r = w4 * 32 + lane;
                         const uint4* qrow = reinterpret_cast<const uint4*>(smem_raw + (s_q - ptx::smem_u32(smem_raw)) + qs * Q_TILE_BYTES + r * 128);
@@ -447,7 +534,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_tc_kernel(const __gr
                         }
                     }
                 }
-                if (args.odd && qt == (int)qtn - 1) ptx::mbar_arrive(b.kv_empty + 8 * (uint32_t)(it % KV_STAGES));
+                if (args.cosign && qt == (int)qtn - 1) ptx::mbar_arrive(b.kv_empty + 8 * (uint32_t)(it % KV_STAGES));
                 ptx::tc_fence_before();
                 if (w4 == 0 && lane == 0) ATT_STAMP(g, 9);
                 ptx::mbar_arrive(b.slot_free + 8 * grp);
@@ -517,6 +604,12 @@ int attention_tc_launch(const void* qkv, void* out, int frames, int tokens, int 
             keys_pad = kp2;
         }
     }
+    args.single = (tokens % QT == 1 && tokens > QT) ? 1 : 0;
+    {
+        static const int single_env = getenv("DISTB200_ATT_SINGLE") ? atoi(getenv("DISTB200_ATT_SINGLE")) : 1;
+        if (!single_env) args.single = 0;
+    }
+    args.cosign = (args.odd || args.single) ? 1 : 0;
     args.keys_ld = keys_ld;
     args.keys_pad = keys_pad;
     args.o_col = (keys_pad / 2 + 31) / 32 * 32;
