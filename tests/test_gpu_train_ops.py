@@ -27,7 +27,7 @@ def _qgelu(x):
 
 
 @pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
-@pytest.mark.parametrize("n", [4096, 1003])
+@pytest.mark.parametrize("n", [4096, 1003, 16000024])
 def test_quickgelu_fwd_bwd(dt, n):
     ops = _ops()
     g = torch.Generator().manual_seed(1)
@@ -42,6 +42,10 @@ def test_quickgelu_fwd_bwd(dt, n):
     assert rel_l2(y32, ref.detach()) < 1e-6
     assert rel_l2(dz32, zz.grad) < 1e-6
     tol = 1e-6 if dt == torch.float32 else 4e-3
+    assert rel_l2(ylp, ref.detach()) < tol and rel_l2(dzlp, zz.grad) < tol
+    # low-precision outputs only (the tensor-core training path): the one-MUFU sigmoid
+    ylp.zero_(); dzlp.zero_()
+    _run(ops.quickgelu(z, None, ylp), ops.quickgelu_bwd(dy, z, None, dzlp))
     assert rel_l2(ylp, ref.detach()) < tol and rel_l2(dzlp, zz.grad) < tol
 
 
