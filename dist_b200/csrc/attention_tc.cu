@@ -167,11 +167,12 @@ struct Bars {   // shared-memory addresses of the mbarriers
     uint32_t kv_full, kv_empty, q_full, q_empty, s_full, p_full, o_full, slot_free, p_early;
 };
 
+template <bool SINGLE>          // SINGLE: the item's last tile holds one query row and is computed on the CUDA cores (args.single)
 __global__ void __launch_bounds__(ATT_THREADS, 1) attention_tc_kernel(const __grid_constant__ AttArgs args) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bar_mem[2 * KV_STAGES + 2 * Q_RING + 10];
     __shared__ uint32_t tmem_slot;
-    __shared__ float sr_p[2][288], sr_red[2][8], sr_o[2][16][HD];      // single-row tiles: scores / probabilities, reductions, partial outputs
+    __shared__ float sr_p[SINGLE ? 2 : 1][SINGLE ? 288 : 1], sr_red[SINGLE ? 2 : 1][8], sr_o[SINGLE ? 2 : 1][SINGLE ? 16 : 1][HD];      // single-row tiles: scores / probabilities, reductions, partial outputs
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int D = args.heads * HD;
@@ -276,7 +277,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_tc_kernel(const __gr
                 const uint32_t sk = s_kv + (uint32_t)st * 2 * kv_bytes;
                 const uint64_t dq = ptx::umma_desc_k_sw128(s_q + qs * Q_TILE_BYTES);
                 const uint32_t ts = tmem + (uint32_t)(slot * args.slot_cols);
-                const bool single = args.single && qt == QTn - 1;          // computed by the softmax group on the CUDA cores: no MMA, same hand-shakes
+                const bool single = SINGLE && qt == QTn - 1;               // computed by the softmax group on the CUDA cores: no MMA, same hand-shakes
                 for (int n0 = 0; n0 < (single ? 0 : args.keys_pad); n0 += 256) {
                     const int nn = min(256, args.keys_pad - n0);
                     const uint32_t idesc = ptx::umma_idesc_bf16(QT, nn);
@@ -302,7 +303,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_tc_kernel(const __gr
                 const uint32_t sv = s_kv + (uint32_t)st * 2 * kv_bytes + kv_bytes;
                 const uint32_t ts = tmem + (uint32_t)(slot * args.slot_cols);
                 const int ks_split = args.split_col < args.keys_pad ? args.split_col / 16 : 0;
-                const bool single = args.single && qt == QTn - 1;
+                const bool single = SINGLE && qt == QTn - 1;
                 if (ks_split > 0) {
                     ptx::mbar_wait(b.p_early + 8 * slot, ph);
                     ptx::tc_fence_after();
@@ -350,7 +351,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_tc_kernel(const __gr
                 if (w4 == 0 && lane == 0) ATT_STAMP(g, 5);
                 float sum = 0.f;
                 float s_x = -INFINITY, p_x = 0.f;
-                if (args.single && qt == (int)qtn - 1) {
+                if (SINGLE && qt == (int)qtn - 1) {
                     // A tile with ONE query row (257 = 2 x 128 + 1) would cost a full S-MMA -> softmax -> PV-MMA chain with one busy
                     // thread.  The group's 128 threads compute the row on the CUDA cores instead, from the swizzled Q / K / V tiles in
                     // shared memory: thread t scores keys t, t+128, ...; (8 columns x 16 key groups) for P V.  The mbarrier hand-shakes
@@ -627,12 +628,14 @@ int attention_tc_launch(const void* qkv, void* out, int frames, int tokens, int 
     static int smem_set_dev[DISTB200_MAX_DEVICES] = {};
     int& smem_set = smem_set_dev[current_device()];
     if (smem > smem_set) {
-        cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         DISTB200_REQUIRE(e == cudaSuccess, "attention(tcgen05): cannot reserve %d bytes of shared memory: %s", smem, cudaGetErrorString(e));
         smem_set = smem;
     }
     const long long grid = args.items < sm_count() ? args.items : sm_count();
-    DISTB200_LAUNCH(attention_tc_kernel, (unsigned)grid, ATT_THREADS, smem, stream, args);
+    if (args.single) DISTB200_LAUNCH(attention_tc_kernel<true>, (unsigned)grid, ATT_THREADS, smem, stream, args);
+    else DISTB200_LAUNCH(attention_tc_kernel<false>, (unsigned)grid, ATT_THREADS, smem, stream, args);
     return check_launch("attention_tc");
 }
 
