@@ -281,7 +281,11 @@ class DistEngine:
             self.set_text_features(text_features)
         self._alloc()
         self.calls = []
+        self.static_calls = []
         self._plan()
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        for c in self.static_calls:                       # weight-only work of the plan (see _plan_head): once per engine
+            c.launch(stream)
         self.graph = None
 
     # ------------------------------------------------------------------------------------------
@@ -638,31 +642,47 @@ class DistEngine:
         F, Mv, H = b * t, b * t * N, a.integration_heads
         add = self.calls.append
         # ---- ada-pooling (dist.py:237-241, 139-162) ----
-        add(ops.rows_bcast(self.sp, Ci, F, Ci, w.agg_sp, 1, False, name="ada.init_sp"))
-        add(ops.rows_bcast(self.top, Ci, b, Ci, w.agg_cls, 1, False, name="ada.init_top"))
+        # The two pooled streams START as the broadcast aggregation tokens (dist.py:237-238), i.e. as constants of the weights: the
+        # broadcasts, and the LayerNorm + query projection of the FIRST ada layer, run once here (`static_calls`) instead of in every
+        # step (six launches); the first layer's output projections take the constant streams as their residual.
+        dev, f32 = self.device, torch.float32
+        self.sp0, self.top0 = torch.zeros(F, Ci, device=dev, dtype=f32), torch.zeros(b, Ci, device=dev, dtype=f32)
+        self.q_s0, self.q_t0 = torch.zeros(F, Ci, device=dev, dtype=self.adt), torch.zeros(b, Ci, device=dev, dtype=self.adt)
+        self.static_calls = [ops.rows_bcast(self.sp0, Ci, F, Ci, w.agg_sp, 1, False, name="ada.init_sp"),
+                             ops.rows_bcast(self.top0, Ci, b, Ci, w.agg_cls, 1, False, name="ada.init_top")]
+        main = self.calls
         for j in range(a.ada_layers):
             e = w.ada[j]
             s, tp = e["sp"], e["tp"]
+            first = j == 0
             # spatial: query = per-frame token, key = value = LN(res + upd)  (clip.py:146-147)
             self._ln(self.res, s["ln"], self.int_a1, in2=self.mid, in2_period=Mv, name="ada.sp.ln_kv")
             self._lin(self.int_a1, s["kv_w"], s["kv_b"], self.kv_s, name="ada.sp.kv")
-            self._ln(self.sp, s["ln"], self.sp_ln, name="ada.sp.ln_q")
-            self._lin(self.sp_ln, s["q_w"], s["q_b"], self.q_s, name="ada.sp.q")
-            add(ops.cross_attention(self.q_s, self.kv_s, self.o_s, F, N, H, name="ada.sp.attn"))
-            self._lin(self.o_s, s["o_w"], s["o_b"], self.sp, res=self.sp, name="ada.sp.out_proj")
+            if first:
+                self.calls = self.static_calls
+            self._ln(self.sp0 if first else self.sp, s["ln"], self.sp_ln, name="ada.sp.ln_q")
+            self._lin(self.sp_ln, s["q_w"], s["q_b"], self.q_s0 if first else self.q_s, name="ada.sp.q")
+            self.calls = main
+            add(ops.cross_attention(self.q_s0 if first else self.q_s, self.kv_s, self.o_s, F, N, H, name="ada.sp.attn"))
+            self._lin(self.o_s, s["o_w"], s["o_b"], self.sp, res=self.sp0 if first else self.sp, name="ada.sp.out_proj")
             self._ln(self.sp, s["ln_out"], self.sp_ln, name="ada.sp.ln_out")
             self._lin(self.sp_ln, s["fc_w"], s["fc_b"], self.mlp_s, act=ops.ACT_QUICKGELU, name="ada.sp.fc")
             self._lin(self.mlp_s, s["pr_w"], s["pr_b"], self.sp, res=self.sp, name="ada.sp.proj")
             # temporal: query = clip token, keys = the t frame tokens + positional embedding (dist.py:155-160)
             self._ln(self.sp, tp["ln"], self.sp_ln, in2=e["pos"], in2_period=t, name="ada.tp.ln_kv")
             self._lin(self.sp_ln, tp["kv_w"], tp["kv_b"], self.kv_t, name="ada.tp.kv")
-            self._ln(self.top, tp["ln"], self.top_ln, name="ada.tp.ln_q")
-            self._lin(self.top_ln, tp["q_w"], tp["q_b"], self.q_t, name="ada.tp.q")
-            add(ops.cross_attention(self.q_t, self.kv_t, self.o_t, b, t, H, name="ada.tp.attn"))
-            self._lin(self.o_t, tp["o_w"], tp["o_b"], self.top, res=self.top, name="ada.tp.out_proj")
+            if first:
+                self.calls = self.static_calls
+            self._ln(self.top0 if first else self.top, tp["ln"], self.top_ln, name="ada.tp.ln_q")
+            self._lin(self.top_ln, tp["q_w"], tp["q_b"], self.q_t0 if first else self.q_t, name="ada.tp.q")
+            self.calls = main
+            add(ops.cross_attention(self.q_t0 if first else self.q_t, self.kv_t, self.o_t, b, t, H, name="ada.tp.attn"))
+            self._lin(self.o_t, tp["o_w"], tp["o_b"], self.top, res=self.top0 if first else self.top, name="ada.tp.out_proj")
             self._ln(self.top, tp["ln_out"], self.top_ln, name="ada.tp.ln_out")
             self._lin(self.top_ln, tp["fc_w"], tp["fc_b"], self.mlp_t, act=ops.ACT_QUICKGELU, name="ada.tp.fc")
             self._lin(self.mlp_t, tp["pr_w"], tp["pr_b"], self.top, res=self.top, name="ada.tp.proj")
+        if a.ada_layers == 0:                             # no pooling layer: the tail reads the constant clip token
+            self.top = self.top0
         # ---- tail (dist.py:242-246) ----
         self._lin(self.clsmean, w.pcls_w, w.pcls_b, self.zbuf, res=self.top, name="tail.proj_spatial_cls")
         self._ln(self.zbuf, w.ln_post, self.z_ln, name="tail.ln_post")
