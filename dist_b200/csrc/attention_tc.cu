@@ -91,6 +91,27 @@ __device__ __forceinline__ float fast_exp2(float x) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+// 2^x for x <= 0 on the FMA / ALU pipes only (no MUFU, no F2I): round-to-nearest split with the 1.5 * 2^23 constant, degree-3 polynomial
+// for 2^f on [-0.5, 0.5] (max relative error 7.7e-5, the probabilities are rounded to bf16 afterwards), exponent added as an integer.
+// Both softmax groups of an SM are in the exponential pass together for most of an item and MUFU.EX2 runs at 16 / clock / SM: every
+// DISTB200_ATT_POLY-th exponential goes here instead (the FlashAttention-4 trick).
+#ifndef DISTB200_ATT_POLY
+#define DISTB200_ATT_POLY 0
+#endif
+__device__ __forceinline__ float poly_exp2(float x) {
+    x = fmaxf(x, -125.0f);
+    const float t = x + 12582912.0f;
+    const float f = x - (t - 12582912.0f);
+    float p = fmaf(f, 0.05508868f, 0.24260405f);
+    p = fmaf(p, f, 0.69327623f);
+    p = fmaf(p, f, 0.99992895f);
+    return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+// idx = position of the element in its (fully unrolled) chunk: the choice folds at compile time
+__device__ __forceinline__ float exp2_sel(float x, int idx) {
+    if (DISTB200_ATT_POLY > 0 && (idx % (DISTB200_ATT_POLY > 0 ? DISTB200_ATT_POLY : 1)) == DISTB200_ATT_POLY - 1) return poly_exp2(x);
+    return fast_exp2(x);
+}
 
 // One query row against all keys of the item on the CUDA cores (see the call site): the 128 threads of a softmax group, Q row / K / V
 // tiles in their 128-byte-swizzled shared-memory layout.  The query row is re-read (broadcast) per key instead of living in 64
@@ -439,8 +460,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_tc_kernel(const __gr
                             uint32_t p[16];
 #pragma unroll
                             for (int i = 0; i < 16; ++i) {
-                                const float e0 = fast_exp2(fmaf(__uint_as_float(hold[hc][2 * i]), c, -mxs));
-                                const float e1 = fast_exp2(fmaf(__uint_as_float(hold[hc][2 * i + 1]), c, -mxs));
+                                const float e0 = exp2_sel(fmaf(__uint_as_float(hold[hc][2 * i]), c, -mxs), 2 * i);
+                                const float e1 = exp2_sel(fmaf(__uint_as_float(hold[hc][2 * i + 1]), c, -mxs), 2 * i + 1);
                                 s0 += e0;
                                 s1 += e1;
                                 p[i] = pack_bf16x2(e0, e1);
@@ -456,8 +477,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_tc_kernel(const __gr
 #pragma unroll
                         for (int i = 0; i < 16; ++i) {
                             const float a0 = fmaf(__uint_as_float(v[2 * i]), c, -mxs), a1 = fmaf(__uint_as_float(v[2 * i + 1]), c, -mxs);
-                            const float e0 = ATT_PROBE(2) ? a0 : fast_exp2(a0);
-                            const float e1 = ATT_PROBE(2) ? a1 : fast_exp2(a1);
+                            const float e0 = ATT_PROBE(2) ? a0 : exp2_sel(a0, 2 * i);
+                            const float e1 = ATT_PROBE(2) ? a1 : exp2_sel(a1, 2 * i + 1);
                             s0 += e0;
                             s1 += e1;
                             p[i] = pack_bf16x2(e0, e1);
