@@ -286,6 +286,8 @@ class DistEngine:
         stream = torch.cuda.current_stream(self.device).cuda_stream
         for c in self.static_calls:                       # weight-only work of the plan (see _plan_head): once per engine
             c.launch(stream)
+        if self.static_calls:
+            torch.cuda.current_stream(self.device).synchronize()       # later forwards may run on another stream
         self.graph = None
 
     # ------------------------------------------------------------------------------------------
