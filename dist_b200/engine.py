@@ -236,12 +236,17 @@ class PackedWeights:
                 entry[tag] = dict(
                     ln=(f32(sd[pre + which + ".ln_1.weight"]), f32(sd[pre + which + ".ln_1.bias"])),
                     q_w=op(wq[:Ci]), q_b=f32(bq[:Ci]), kv_w=op(wq[Ci:]), kv_b=f32(bq[Ci:]),
+                    # K / V projection on the NORMALISED rows (unit affine): W diag(gamma), b + W beta.  Every ada layer normalises the same
+                    # tensor (res + upd of the last DiST layer, dist.py:239-241), so one LayerNorm pass serves all of them.
+                    kv_wn=op(wq[Ci:].detach().double().cpu() * sd[pre + which + ".ln_1.weight"].detach().double().cpu()[None, :]),
+                    kv_bn=f32(bq[Ci:].detach().double().cpu() + wq[Ci:].detach().double().cpu() @ sd[pre + which + ".ln_1.bias"].detach().double().cpu()),
                     o_w=op(sd[pre + which + ".attn.out_proj.weight"]), o_b=f32(sd[pre + which + ".attn.out_proj.bias"]),
                     ln_out=(f32(sd[pre + ln_out + ".weight"]), f32(sd[pre + ln_out + ".bias"])),
                     fc_w=op(sd[pre + mlp + ".c_fc.weight"]), fc_b=f32(sd[pre + mlp + ".c_fc.bias"]),
                     pr_w=op(sd[pre + mlp + ".c_proj.weight"]), pr_b=f32(sd[pre + mlp + ".c_proj.bias"]),
                 )
             self.ada.append(entry)
+        self.unit_ln = (f32(torch.ones(Ci)), f32(torch.zeros(Ci)))
         self.agg_cls = f32(sd["dist_net.aggregated_cls_token"].float().reshape(1, Ci))
         self.agg_sp = f32(sd["dist_net.aggregated_spatial_cls_token"].float().reshape(1, Ci))
         self.pcls_w = op(sd["dist_net.proj_spatial_cls_token.weight"])
@@ -658,8 +663,9 @@ class DistEngine:
             s, tp = e["sp"], e["tp"]
             first = j == 0
             # spatial: query = per-frame token, key = value = LN(res + upd)  (clip.py:146-147)
-            self._ln(self.res, s["ln"], self.int_a1, in2=self.mid, in2_period=Mv, name="ada.sp.ln_kv")
-            self._lin(self.int_a1, s["kv_w"], s["kv_b"], self.kv_s, name="ada.sp.kv")
+            if first:                                   # x_hat of res + upd, once for all ada layers (their LayerNorm affines are folded into kv_wn / kv_bn)
+                self._ln(self.res, w.unit_ln, self.int_a1, in2=self.mid, in2_period=Mv, name="ada.sp.ln_kv")
+            self._lin(self.int_a1, s["kv_wn"], s["kv_bn"], self.kv_s, name="ada.sp.kv")
             if first:
                 self.calls = self.static_calls
             self._ln(self.sp0 if first else self.sp, s["ln"], self.sp_ln, name="ada.sp.ln_q")
