@@ -18,6 +18,9 @@ SHAPES = {  # name: (N, K, act, residual, out dtype, out2)
     "proj": (768, 768, False, True, torch.float32, False),
     "fc1": (3072, 768, True, False, torch.bfloat16, False),
     "fc2": (768, 3072, False, True, torch.float32, True),
+    "proj2": (768, 768, False, True, torch.float32, True),          # the planned out_proj: fp32 stream in place + bf16 copy
+    "proj2_nores": (768, 768, False, False, torch.float32, True),   # same stores, no residual read
+    "proj_bf": (768, 768, False, False, torch.bfloat16, False),     # bf16 store only
     "plain": (3072, 768, False, False, torch.bfloat16, False),
     "nobias": (3072, 768, False, False, torch.bfloat16, False),
 }
